@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the MGProto Gaussian-prototype hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (driver: torchrun for N > 1)
+    python bench.py --impl reference ...                     (CPU arm: the reference algorithm on host cores)
+
+Workload (BASELINE.json configs[1], named in config.workload): per GPU a batch of 256 images'
+add-on feature maps [256,128,14,14] against a 200-class x 10-prototype x 128-d diagonal-Gaussian
+mixture, T=20 mining levels, a full 800-row/class memory bank.  One *step* is one pass of the
+training hot path over one batch: normalise -> log-likelihood -> top-T mining -> pi-mix logits
+-> loss -> backward to the features -> bank enqueue -> update_GMM (3 EM loops, sequential Adam).
+The backbone is outside the path and is not timed.
+
+  value   images/s, whole job, inputs resident in HBM
+  e2e     images/s through MGProto.head()/update_GMM() with HOST (pinned) feature batches: H2D of the
+          features and D2H of the logits inside the timed region, synchronised every step
+  roofline  the log-likelihood kernel (mgp_logprob_fwd, [N,P] output: the north-star kernel), timed
+          alone with CUDA events: algorithmic bytes 4*(N*D + 2*P*D + N*P) per launch / duration,
+          against MEASURED_PEAKS.json's HBM copy bandwidth (burst figure: kernel timed alone)
+  cpu_baseline  the oracle port of the reference algorithm on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=256, C=200, K=10, D=128, H=14, W=14, T=20, cap=800)
+N_ROT = 8   # distinct input batches rotated through (8 x 25.7 MB of features > the 126 MB L2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step(n_img, seed=0, with_em=True):
+    """One bounded-sample step of the reference algorithm (oracle port, numpy) -> seconds."""
+    import numpy as np
+    from oracle import mgproto_oracle as O
+    c = CFG
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n_img, c["D"], c["H"], c["W"])).astype(np.float32)
+    mu = O.l2_normalize(rng.random((c["C"], c["K"], c["D"])).astype(np.float32), axis=2)
+    sg = np.full_like(mu, 1 / np.sqrt(2 * np.pi))
+    wt = np.zeros((c["C"], c["C"] * c["K"]), np.float32)
+    for i in range(c["C"]):
+        wt[i, i * c["K"]:(i + 1) * c["K"]] = 1.0 / c["K"]
+    gt = rng.integers(0, c["C"], size=(n_img,))
+    t0 = time.perf_counter()
+    fw = O.head_forward(x, mu, sg, wt, gt, c["T"])
+    rows = O.enqueue_rows(fw["xhat"], fw["idx"], gt, c["C"], c["K"], c["H"] * c["W"])
+    if with_em:
+        bank = O.MemoryBankOracle(c["C"], c["D"], c["cap"])
+        upd = np.zeros(c["C"], bool)
+        for cc, r in rows:
+            bank.data[cc] = O.l2_normalize(mu[cc][rng.integers(0, c["K"], c["cap"])] +
+                                           0.3 * rng.standard_normal((c["cap"], c["D"])).astype(np.float32), axis=1)
+            bank.mem_len[cc] = c["cap"]
+            bank.push(cc, r)
+            upd[cc] = True
+        adam = O.AdamOracle(mu.shape, lr=3e-3, dtype=np.float32)
+        O.update_gmm(bank, upd, mu, sg, wt, adam)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img = 2
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(n_img)
+    ts = [cpu_reference_step(n_img, seed=s) for s in range(max(1, min(args.steps, 5)))]
+    t = statistics.mean(ts)
+    val = n_img / t
+    c = CFG
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": len(ts), "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(args.gpus),
+        "pairs_per_sec": val * c["H"] * c["W"] * c["C"] * c["K"],
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": 1, "kind": "port",
+                         "sample": "%d images of the 256-image batch per step, full 200x10x128 mixture, forward + "
+                                   "enqueue + update_GMM of the touched classes; numpy oracle port "
+                                   "(the Python reference cannot travel to the GPU box)" % n_img},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def _config(n_gpus):
+    c = CFG
+    return {"workload": "BASELINE.json configs[1]: batch %d/GPU add-on feature maps [%d,%d,%d,%d], %dx%dx%d diag-Gaussian "
+                        "mixture, T=%d, bank %d rows/class; step = head fwd+bwd + enqueue + update_GMM"
+                        % (c["B"], c["B"], c["D"], c["H"], c["W"], c["C"], c["K"], c["D"], c["T"], c["cap"]),
+            "global_batch": c["B"] * n_gpus, "parallelism": "dp%d (image-sharded, EM stats all-reduce)" % n_gpus,
+            "l2": "inputs rotate through %d distinct batches (%.0f MB) + 401 MB intermediate > 126 MB L2"
+                  % (N_ROT, N_ROT * c["B"] * c["D"] * c["H"] * c["W"] * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(dev, seed=0):
+    import torch
+    import torch.nn as nn
+    import mgproto_b200 as M
+    c = CFG
+    g = torch.Generator().manual_seed(seed)
+    net = M.MGProto(features=nn.Sequential(nn.Conv2d(3, 8, 1)), img_size=224, prototype_shape=(c["C"] * c["K"], c["D"], 1, 1),
+                    proto_layer_rf_info=None, num_classes=c["C"], add_on_layers_type="regular", sz_embedding=32,
+                    mem_capacity=c["cap"], mine_K=c["T"])
+    mu = M.l2_normalize(torch.rand(c["C"], c["K"], c["D"], generator=torch.Generator().manual_seed(2)), dim=2)
+    net.prototype_means.data.copy_(mu)
+    net = net.to(dev)
+    # every class's bank full: rows = l2_normalize(mu_ck + 0.3 randn)
+    g6 = torch.Generator().manual_seed(6)
+    kk = torch.randint(0, c["K"], (c["C"], c["cap"]), generator=g6)
+    rows = mu[torch.arange(c["C"])[:, None], kk] + 0.3 * torch.randn(c["C"], c["cap"], c["D"], generator=g6)
+    net.queue.bank.copy_(M.l2_normalize(rows, dim=2).to(dev))
+    net.queue.mem_len.fill_(c["cap"])
+    net.prototype_optimizer = torch.optim.Adam([{"params": net.prototype_means, "lr": 3e-3}])
+    net.train()
+    return net
+
+
+def loss_fn(out, gt):
+    import torch.nn.functional as F
+    ce0 = F.cross_entropy(out[:, :, 0], gt)
+    mine = sum(F.cross_entropy(out[:, :, k], gt) for k in range(1, out.shape[2])) / (out.shape[2] - 1)
+    return ce0 + 0.2 * mine                                   # ref train_and_test.py:37-41, :55
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mgproto_b200 import ops, parallel
+    c = CFG
+    W = max(3, args.warmup)
+    net = build_model(dev)
+    net.math_mode = args.math
+    if world > 1:
+        parallel.attach(net)
+    B, D, H, Wd, HW = c["B"], c["D"], c["H"], c["W"], c["H"] * c["W"]
+    gen = torch.Generator().manual_seed(1 + rank)
+    feats_host = [torch.randn(B, D, H, Wd, generator=gen).pin_memory() for _ in range(N_ROT)]
+    gts = [torch.randint(0, c["C"], (B,), generator=gen).to(dev) for _ in range(N_ROT)]
+    feats = [f.to(dev) for f in feats_host]
+
+    def step(x, gt):
+        x.grad = None
+        x.requires_grad_(True)
+        out = net.head(x, gt)
+        loss = loss_fn(out, gt)
+        loss.backward()
+        net.update_GMM()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------
+    for i in range(W):
+        step(feats[i % N_ROT], gts[i % N_ROT])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(feats[i % N_ROT], gts[i % N_ROT])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm)
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- end to end: host buffers in, logits out ---------------------------------------------
+    x_dev = torch.empty(B, D, H, Wd, device=dev)
+    out_host = torch.empty(B, c["C"], c["T"], pin_memory=True)
+
+    def e2e_step(i):
+        x_dev.requires_grad_(False)
+        x_dev.copy_(feats_host[i % N_ROT], non_blocking=True)
+        out = step(x_dev, gts[i % N_ROT])
+        out_host.copy_(out.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * args.steps / (float(tm) / 1e3)
+
+    # ---- roofline of the log-likelihood kernel (timed alone, rank 0) --------------------------
+    roof = None
+    extra = {}
+    if rank == 0:
+        peak, how = peaks()
+        P, N = c["C"] * c["K"], B * HW
+        mu = net.prototype_means.detach().reshape(P, D).contiguous()
+        sg = net.prototype_covs.detach().reshape(P, D).contiguous()
+        xs = [ops.normalize_fwd(f)[0] for f in feats[:6]]                     # 6 x 25.7 MB inputs rotate
+        for i in range(3):
+            ops.logprob(xs[i % 6], mu, sg, 0, math=args.math)
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record()
+        for i in range(reps):
+            ops.logprob(xs[i % 6], mu, sg, 0, math=args.math)
+        e1.record()
+        torch.cuda.synchronize()
+        t_ka = e0.elapsed_time(e1) / reps / 1e3
+        abytes = 4.0 * (N * D + 2 * P * D + N * P)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("logprob_dram_bytes_per_launch")
+        roof = {"kernel": "mgp_logprob_fwd [N,P] (%s)" % args.math, "bound": "hbm", "achieved": abytes / t_ka / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": abytes / t_ka / 1e9 / peak, "traffic": traffic,
+                "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst: kernel timed alone)",
+                "us_per_launch": t_ka * 1e6, "algorithmic_bytes": abytes,
+                "pairs_per_sec": N * P / t_ka, "tensor_tflops_equiv": 4.0 * N * P * D / t_ka / 1e12}
+        # EM statistics kernel, same treatment (second kernel the north star names)
+        order = torch.arange(c["C"], dtype=torch.int32, device=dev)
+        stats = torch.empty(c["C"], net.em_n_split, ops.em_stat_stride(c["K"], D), device=dev)
+        wt = net.last_layer.weight.data
+        for _ in range(3):
+            ops.em_stats(net.queue.bank, order, net.prototype_means.data, net.prototype_covs.data, wt, 0.1, stats,
+                         net.em_n_split)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ops.em_stats(net.queue.bank, order, net.prototype_means.data, net.prototype_covs.data, wt, 0.1, stats,
+                         net.em_n_split)
+        e1.record()
+        torch.cuda.synchronize()
+        t_em = e0.elapsed_time(e1) / reps / 1e3
+        eb = 4.0 * c["C"] * c["cap"] * D
+        extra["roofline_em_stats"] = {"kernel": "mgp_em_stats (200 classes x 800 rows)", "bound": "hbm",
+                                      "achieved": eb / t_em / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": eb / t_em / 1e9 / peak, "us_per_launch": t_em * 1e6,
+                                      "note": "bank (82 MB) fits in L2 across repeats: upper-bound figure"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        n_img = 2
+        cpu_reference_step(n_img)
+        ts = [cpu_reference_step(n_img, seed=s) for s in range(3)]
+        cpu = {"value": n_img / statistics.mean(ts), "unit": "images/s", "cores": 1, "kind": "port",
+               "sample": "%d images/step x 3 steps of the same workload (forward + enqueue + update_GMM of the touched "
+                         "classes), numpy oracle port of the reference algorithm" % n_img}
+
+    if rank == 0:
+        line = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(world),
+            "pairs_per_sec": value * HW * c["C"] * c["K"],
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * D * HW * 4,
+                    "d2h_bytes_per_step": B * c["C"] * c["T"] * 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "math": args.math,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

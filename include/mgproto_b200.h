@@ -1,0 +1,188 @@
+/*
+ * mgproto_b200 -- C ABI of the B200-native MGProto Gaussian-prototype hot path.
+ *
+ * The reference (cwangrun/MGProto) has no FFI: its boundary is the Python surface of
+ * model.MGProto.  Each entry point below replaces the reference code
+ * cited beside it ("ref:" = file:line under /root/reference) and is what a binding of
+ * that path calls.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 unless stated), dense, row-major, 16-byte
+ *     aligned; the caller (PyTorch) owns all memory, nothing is allocated or retained;
+ *   - kernels are enqueued asynchronously on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = launched; >0 = the cudaError_t of the failing call;
+ *     <0 = an MGP_ERR_* argument error, nothing launched.  Nothing throws.
+ *   - symbols: B images, HW patches/image, N = B*HW, C classes, K prototypes/class,
+ *     P = C*K, D feature dim (D % 4 == 0), T mining levels (T <= 32, T <= HW), cap = bank
+ *     rows per class.  "sigma" holds standard deviations (ref: model.py:272).
+ */
+#ifndef MGPROTO_B200_H_
+#define MGPROTO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGP_ABI_VERSION 1
+
+#define MGP_OK 0
+#define MGP_ERR_INVALID (-1)      /* null pointer / non-positive size / misalignment      */
+#define MGP_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels are built for          */
+#define MGP_ERR_WORKSPACE (-3)    /* workspace too small (see the *_ws_bytes queries)      */
+
+/* math modes of the log-probability kernels */
+#define MGP_MATH_FP32 0     /* exact-form fp32 SIMT: sum_d ((x-mu)/(sigma+eps))^2          */
+#define MGP_MATH_TC 1       /* tcgen05 tensor cores, fp16 hi/lo split x3, fp32 accumulate  */
+#define MGP_MATH_AUTO 2     /* TC when the shape qualifies, else FP32                      */
+
+/* output layouts of mgp_logprob_fwd */
+#define MGP_OUT_LOGP_NP 0      /* out[n*P + p]           = log p      (ref: compute_log_prob)   */
+#define MGP_OUT_LOGP_BPHW 1    /* out[(b*P + p)*HW + hw] = log p      (feeds mgp_head_select)    */
+#define MGP_OUT_NEGP_BPHW 2    /* out[(b*P + p)*HW + hw] = -exp(log p) (ref: push_forward :437)  */
+
+int mgp_abi_version(void);
+const char* mgp_error_string(int code);
+/* 1 if the library was built with the sm_100a tcgen05 kernels */
+int mgp_has_tensor_core_path(void);
+
+/* ---- a1  l2_normalize + rearrange -------------------------------------------------------
+ * ref: model.py:40-41, :210-211, :431-432.
+ * x_nchw [B,D,HW] -> xhat_nd [N,D] = x / max(||x||_2, 1e-12) over D; inv_norm [N] = 1/max(..).
+ * xhat_nchw (optional, may be NULL) receives the same values in [B,D,HW] (push_forward's
+ * first return value). */
+int mgp_normalize_fwd(const float* x_nchw, float* xhat_nd, float* inv_norm, float* xhat_nchw,
+                      int B, int D, int HW, void* stream);
+
+/* Backward of the above: g_xhat_nd [N,D] -> g_x_nchw [B,D,HW]
+ *   g_x = (g - xhat * <xhat, g>) * inv_norm. */
+int mgp_normalize_bwd(const float* g_xhat_nd, const float* xhat_nd, const float* inv_norm,
+                      float* g_x_nchw, int B, int D, int HW, void* stream);
+
+/* ---- a2/a3/a16  diagonal-Gaussian log-likelihood -----------------------------------------
+ * ref: model.py:256-275 (compute_log_prob, eps = 0), :323-336 (_estimate_log_prob,
+ * eps = 1e-10, log(sigma+eps)), :429-438 (push_forward).
+ *   log p[n,p] = -D/2 log 2pi - sum_d log(sigma+eps_log) - 1/2 sum_d ((x-mu)/(sigma+eps))^2
+ * `eps` is added to sigma inside the quotient; `eps_log` inside the logarithm
+ * (compute_log_prob: 0 / 0, _estimate_log_prob: 1e-10 / 1e-10).
+ * xhat_nd [N,D] (N = B*HW; for MGP_OUT_LOGP_NP pass B = N, HW = 1 if there is no image
+ * structure), mu/sigma [P,D]; `ws` is scratch of at least mgp_logprob_ws_bytes(P, D, math). */
+size_t mgp_logprob_ws_bytes(int P, int D, int math);
+int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const float* sigma, float eps,
+                    float eps_log, float* out, int out_layout, int B, int HW, int P, int D,
+                    int math, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a4-a7  top-T mining + mixture logits ------------------------------------------------
+ * ref: model.py:188-206 (global_max_pooling_gmm_topT), :214-222, :254, NonNegLinear :54-74.
+ * logp_bphw [B,P,HW] (MGP_OUT_LOGP_BPHW).  Per (b,p): the T largest over HW, descending
+ * (ties: smaller index first) -> vals [B,P,T] = exp(log p) (BEFORE the wrong-class rule),
+ * idx [B,P,T] int32.  Then logits[b,c,t] = log sum_k W[c, c*K+k] * v'[b,c*K+k,t] with
+ * v'[.,t] = v[.,0] for prototypes of classes != gt[b] and t >= 1 (gt may be NULL: no rule).
+ * weight_cp is last_layer.weight [C, P]; only its class-diagonal blocks are read. */
+int mgp_head_select(const float* logp_bphw, const float* weight_cp, const int64_t* gt,
+                    float* logits, float* vals, int32_t* idx, int B, int HW, int C, int K,
+                    int T, void* stream);
+
+/* Backward of mgp_head_select composed with the log-likelihood and the normalisation:
+ * grad_logits [B,C,T] -> g_x_nchw [B,D,HW] (gradient w.r.t. the un-normalised features;
+ * mu, sigma receive none: they are detached at ref model.py:264-265).  Autograd of the
+ * reference saves N*P*D*4 bytes for this (51 GB at B=256); here only vals/idx/logits are
+ * kept and the T selected patches per (b,p) are re-differentiated.
+ * ws: scratch of mgp_head_bwd_ws_bytes(B, HW, P, D) bytes. */
+size_t mgp_head_bwd_ws_bytes(int B, int HW, int P, int D);
+int mgp_head_bwd(const float* grad_logits, const float* logits, const float* vals,
+                 const int32_t* idx, const float* weight_cp, const int64_t* gt,
+                 const float* xhat_nd, const float* inv_norm, const float* mu,
+                 const float* sigma, void* ws, size_t ws_bytes, float* g_x_nchw, int B, int HW,
+                 int C, int K, int D, int T, void* stream);
+
+/* ---- a8/a9  enqueue into the per-class FIFO bank -----------------------------------------
+ * ref: model.py:225-250, utils/memory.py:31-73.
+ *
+ * mgp_mined_gather: for every image, the top-1 patch (level 0 of idx [B,P,T]) of each of its
+ * GT class's K prototypes: top1 [B,K] int32 spatial index, rows [B,K,D] feature rows.  (These
+ * two small tensors are what a batch-sharded multi-GPU run all-gathers before the enqueue.)
+ *
+ * mgp_bank_enqueue: per image, the rows at the unique (ascending) spatial indices are appended
+ * to the image's class FIFO (classes independent; within a class: image order, then ascending
+ * index -- the reference's order).  The bank is a ring: bank [C,cap,D], logical row r of class c
+ * lives at slot (head[c] + r) % cap, r < mem_len[c] (oldest first).  A single push larger than
+ * cap keeps its first cap rows (the reference draws an unseeded random subset there).
+ * updated[c] (uint8) is set for every class that received rows (ref model.py:250).
+ * plan [B*K] int32 is scratch.  gt outside [0,C) skips the image. */
+int mgp_mined_gather(const float* xhat_nd, const int32_t* idx, const int64_t* gt, int32_t* top1,
+                     float* rows, int B, int HW, int C, int K, int D, int T, void* stream);
+int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, uint8_t* updated,
+                     const float* rows, const int32_t* top1, const int64_t* gt, int32_t* plan,
+                     int B, int C, int K, int D, int cap, void* stream);
+
+/* Copies the ring of every class into oldest->newest order: lin [C,cap,D] (rows >= mem_len
+ * zero).  This is the layout of the reference's queue.cls%d buffers (state_dict wire format). */
+int mgp_bank_linearize(const float* bank, const int64_t* mem_len, const int32_t* head,
+                       float* lin, int C, int cap, int D, void* stream);
+
+/* ---- a10-a12  memory-bank EM ---------------------------------------------------------------
+ * ref: model.py:277-301 (update_GMM), :303-321 (_e_step), :367-401 (_m_step_diversified).
+ *
+ * mgp_em_plan: active[c] = updated[c] && mem_len[c] >= cap (ref :283,:289); order[c] = rank of
+ * c among the active classes (ascending id) or -1; sched[0] = number of active classes,
+ * sched[1] = Adam step count before this update (adam_step[0] if a device counter is given,
+ * which is then advanced by num_em_loop * n_active; else the host value step0); updated[]
+ * is cleared (ref :287,:301).  No host sync.
+ *
+ * mgp_em_stats: E-step + sufficient statistics of the smoothed responsibilities over bank
+ * slots [row_begin, row_end) of every active class (a row shard; 0, cap = all):
+ *   r_nk = (softmax_k(lp_nk + log(pi_k + 1e-10)) + alpha) / sum_k(.)
+ *   stats[c][split] = { S0[K], S1[K][D], S2[K][D] (if with_s2), loglik }   (partial sums)
+ * stats layout [C][n_split][stat_stride], stat_stride = mgp_em_stat_stride(K, D, with_s2);
+ * partials are combined in split order by mgp_em_update (deterministic; a multi-GPU caller
+ * all-reduces the whole buffer first).  pi is read from weight_cp's class-diagonal blocks.
+ *
+ * mgp_em_update: the diversified M-step with the reference's sequential semantics in one
+ * launch for all classes.  The reference takes one Adam step on the WHOLE mu tensor per
+ * (active class, EM loop) with a gradient that is zero outside that class, so per class the
+ * timeline is: num_em_loop*order[c] zero-gradient steps (phase 0; inactive classes take all
+ * their zero-gradient steps here), the EM-loop steps (phase 1, em_loop = 0..num_em_loop-1,
+ * each after a fresh mgp_em_stats): gradient -(S1 - mu S0) w / n + lamda * diversity gradient,
+ * Adam step, pi <- tau*pi + (1-tau)*(S0+1e-10)/n written into weight_cp; then the trailing
+ * zero-gradient steps (phase 2).  Adam arithmetic is torch.optim.Adam's (no weight decay, no
+ * amsgrad); exp_avg / exp_avg_sq [C,K,D].  With exp_avg == NULL no optimiser step is taken
+ * (phase 1 then only writes grad_out [C,K,D] and pi: for a caller-owned optimiser);
+ * only_class >= 0 restricts phase 1 to that class. */
+size_t mgp_em_stat_stride(int K, int D, int with_s2);
+int mgp_em_plan(uint8_t* updated, const int64_t* mem_len, int32_t* order, int32_t* sched,
+                int32_t* adam_step, int step0, int C, int cap, int num_em_loop, void* stream);
+int mgp_em_stats(const float* bank, const int32_t* order, const float* mu, const float* sigma,
+                 const float* weight_cp, float alpha, int row_begin, int row_end, int n_split,
+                 int with_s2, float* stats, int C, int K, int D, int cap, void* stream);
+int mgp_em_update(const float* stats, int n_split, int with_s2, int n_rows_total,
+                  const int32_t* order, const int32_t* sched, float* mu, const float* sigma,
+                  float* weight_cp, float* exp_avg, float* exp_avg_sq, int em_loop,
+                  int num_em_loop, int phase, float lr, float beta1, float beta2, float adam_eps,
+                  float tau, float lamda, float* grad_out, int only_class, int C, int K, int D,
+                  void* stream);
+
+/* ---- a11/a13/a14  EM building blocks on explicit rows ---------------------------------------
+ * ref: model.py:303-321 (_e_step), :338-365 (_m_step), :403-421 (_score).
+ * x [n,D], mu/sigma [K,D], pi [K]  ->  log_resp [n,K], score [n] = logsumexp_k(lp+log(pi+1e-10)).
+ * Either output may be NULL. */
+int mgp_em_estep(const float* x, const float* mu, const float* sigma, const float* pi,
+                 float* log_resp, float* score, int n, int K, int D, void* stream);
+/* closed-form M-step from log_resp (the only sigma update in the reference):
+ * pi_out [K], mu_out [K,D], sigma_out [K,D]. */
+int mgp_em_mstep_closed(const float* x, const float* log_resp, float alpha, float* pi_out,
+                        float* mu_out, float* sigma_out, int n, int K, int D, void* stream);
+
+/* ---- f1  prototype projection search --------------------------------------------------------
+ * ref: push.py:125-158.  For every image and the K prototypes of its label's class: flat HW
+ * argmin of -p (= argmax of log p; ties: smaller index) and -p there.
+ * logp_bphw [B,P,HW] -> arg [B,K] int32, val [B,K]. */
+int mgp_push_argmin(const float* logp_bphw, const int64_t* labels, int32_t* arg, float* val,
+                    int B, int HW, int C, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGPROTO_B200_H_ */

@@ -1,0 +1,70 @@
+// C-ABI glue: version / error strings and the log-likelihood dispatcher.
+#include "mgp_common.cuh"
+
+int mgp_logprob_simt_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log,
+                            float* out, int layout, int B, int HW, int P, int D, float* ws, cudaStream_t st);
+// logprob_tc.cu
+bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D);
+size_t mgp_logprob_tc_ws_bytes(int P, int D);
+int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log,
+                          float* out, int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes,
+                          cudaStream_t st);
+
+extern "C" int mgp_abi_version(void) { return MGP_ABI_VERSION; }
+
+extern "C" const char* mgp_error_string(int code) {
+    switch (code) {
+        case MGP_OK: return "ok";
+        case MGP_ERR_INVALID: return "mgproto_b200: invalid argument (null pointer, non-positive size or misalignment)";
+        case MGP_ERR_UNSUPPORTED: return "mgproto_b200: shape not supported by the sm_100a kernels";
+        case MGP_ERR_WORKSPACE: return "mgproto_b200: workspace too small";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "mgproto_b200: unknown error";
+}
+
+extern "C" int mgp_has_tensor_core_path(void) {
+#ifdef MGP_WITH_TC
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+extern "C" size_t mgp_logprob_ws_bytes(int P, int D, int math) {
+    size_t simt = ((size_t)P * D + P) * sizeof(float);
+#ifdef MGP_WITH_TC
+    if (math != MGP_MATH_FP32) {
+        size_t tc = mgp_logprob_tc_ws_bytes(P, D);
+        return tc > simt ? tc : simt;
+    }
+#endif
+    (void)math;
+    return simt;
+}
+
+extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const float* sigma, float eps, float eps_log,
+                               float* out, int out_layout, int B, int HW, int P, int D, int math, void* ws,
+                               size_t ws_bytes, void* stream) {
+    if (!xhat_nd || !mu || !sigma || !out || !ws) return MGP_ERR_INVALID;
+    if (B <= 0 || HW <= 0 || P <= 0 || D <= 0 || (D & 3)) return MGP_ERR_INVALID;
+    if (out_layout < MGP_OUT_LOGP_NP || out_layout > MGP_OUT_NEGP_BPHW) return MGP_ERR_INVALID;
+    if (!mgp_aligned16(xhat_nd) || !mgp_aligned16(mu) || !mgp_aligned16(sigma) || !mgp_aligned16(out) ||
+        !mgp_aligned16(ws))
+        return MGP_ERR_INVALID;
+    if ((long long)B * HW > 0x7fffffffLL) return MGP_ERR_UNSUPPORTED;
+    if (ws_bytes < mgp_logprob_ws_bytes(P, D, math)) return MGP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+#ifdef MGP_WITH_TC
+    if (math == MGP_MATH_TC || math == MGP_MATH_AUTO) {
+        if (mgp_logprob_tc_supported(out_layout, B, HW, P, D))
+            return mgp_logprob_tc_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D, ws, ws_bytes, st);
+        if (math == MGP_MATH_TC) return MGP_ERR_UNSUPPORTED;
+    }
+#else
+    if (math == MGP_MATH_TC) return MGP_ERR_UNSUPPORTED;
+#endif
+    return mgp_logprob_simt_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D,
+                                   reinterpret_cast<float*>(ws), st);
+}

@@ -1,0 +1,185 @@
+// a8/a9: enqueue of the mined top-1 patches into the per-class FIFO memory bank.
+// ref: model.py:225-250 (dedupe per image, class-ascending, image order), utils/memory.py:31-73
+// (FIFO with eviction of the oldest rows).
+//
+// The reference keeps each class buffer physically ordered oldest->newest by shifting it on
+// every push and runs ~B*K host-synchronising torch.unique / torch.where calls; here the bank
+// is one [C, cap, D] ring (head[c], mem_len[c]) and an iteration's enqueue is two launches with
+// no host synchronisation: a single-CTA planner (dedupe, per-class offsets, ring arithmetic)
+// and a row scatter.  Row order inside a class does not change any EM result except through
+// fp32 summation order; mgp_bank_linearize reproduces the reference layout on demand.
+#include "mgp_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(1024)
+enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, uint8_t* __restrict__ updated,
+                    const int32_t* __restrict__ top1_bk, const int64_t* __restrict__ gt, int32_t* __restrict__ plan,
+                    int B, int C, int K, int cap) {
+    extern __shared__ int sm[];
+    int* ucount = sm;       // [B] unique rows of image b
+    int* cls = sm + B;      // [B] class or -1
+    int* wr_m = sm + 2 * B; // [B] rows accepted for the class if b is the class's first image, else -1
+    constexpr int T = 1;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const long long c = gt[b];
+        if (c < 0 || c >= C) {
+            cls[b] = -1;
+            ucount[b] = 0;
+            for (int k = 0; k < K; ++k) plan[b * K + k] = -1;
+            continue;
+        }
+        cls[b] = (int)c;
+        const int32_t* top1 = top1_bk + (size_t)b * K;
+        int u = 0;
+        for (int k = 0; k < K; ++k) {
+            const int v = top1[(size_t)k * T];
+            bool first = true;
+            for (int k2 = 0; k2 < k; ++k2) first = first && (top1[(size_t)k2 * T] != v);
+            int rank = -1;
+            if (first) {
+                rank = 0;  // number of distinct smaller values = ascending position (torch.unique order)
+                for (int k2 = 0; k2 < K; ++k2) {
+                    const int v2 = top1[(size_t)k2 * T];
+                    if (v2 < v) {
+                        bool f2 = true;
+                        for (int k3 = 0; k3 < k2; ++k3) f2 = f2 && (top1[(size_t)k3 * T] != v2);
+                        rank += f2 ? 1 : 0;
+                    }
+                }
+                ++u;
+            }
+            plan[b * K + k] = rank;
+        }
+        ucount[b] = u;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int c = cls[b];
+        if (c < 0) continue;
+        int off = 0, tot = 0;
+        bool first_of_class = true;
+        for (int b2 = 0; b2 < B; ++b2) {
+            if (cls[b2] == c) {
+                if (b2 < b) { off += ucount[b2]; first_of_class = false; }
+                tot += ucount[b2];
+            }
+        }
+        const int len = (int)mem_len[c];
+        const int hd = head[c];
+        const int m = min(tot, cap);
+        for (int k = 0; k < K; ++k) {
+            const int r = plan[b * K + k];
+            int slot = -1;
+            if (r >= 0 && off + r < m) slot = (hd + len + off + r) % cap;
+            plan[b * K + k] = slot;
+        }
+        // every reader of mem_len/head for class c sees the same old values; publish after the barrier
+        wr_m[b] = first_of_class ? m : -1;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int c = cls[b];
+        if (c < 0) continue;
+        const int m = wr_m[b];
+        if (m <= 0) continue;
+        const int len = (int)mem_len[c];
+        const int hd = head[c];
+        if (len + m <= cap) {
+            mem_len[c] = len + m;
+        } else {
+            head[c] = (hd + (len + m - cap)) % cap;
+            mem_len[c] = cap;
+        }
+        updated[c] = 1;                                                     // ref model.py:250
+    }
+}
+
+// top-1 patch of each of the GT class's K prototypes: spatial index and feature row
+__global__ void mined_gather_kernel(const float* __restrict__ xhat, const int32_t* __restrict__ idx,
+                                    const int64_t* __restrict__ gt, int32_t* __restrict__ top1,
+                                    float* __restrict__ rows, int B, int HW, int C, int K, int D, int T) {
+    const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wg >= B * K) return;
+    const int b = wg / K, k = wg - b * K;
+    const long long c = gt[b];
+    float4* dst = reinterpret_cast<float4*>(rows + (size_t)wg * D);
+    if (c < 0 || c >= C) {
+        if (lane == 0) top1[wg] = -1;
+        for (int d = lane; d < D / 4; d += 32) dst[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int n = idx[((size_t)b * C * K + (size_t)c * K + k) * T];     // level 0 (ref model.py:225-226)
+    if (lane == 0) top1[wg] = n;
+    const float4* src = reinterpret_cast<const float4*>(xhat + ((size_t)b * HW + n) * D);
+    for (int d = lane; d < D / 4; d += 32) dst[d] = src[d];
+}
+
+__global__ void enqueue_scatter_kernel(float* __restrict__ bank, const float* __restrict__ rows,
+                                       const int64_t* __restrict__ gt, const int32_t* __restrict__ plan, int B, int K,
+                                       int D, int cap) {
+    const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wg >= B * K) return;
+    const int slot = plan[wg];
+    if (slot < 0) return;
+    const long long c = gt[wg / K];
+    const float4* src = reinterpret_cast<const float4*>(rows + (size_t)wg * D);
+    float4* dst = reinterpret_cast<float4*>(bank + ((size_t)c * cap + slot) * D);
+    for (int d = lane; d < D / 4; d += 32) dst[d] = src[d];
+}
+
+__global__ void bank_linearize_kernel(const float* __restrict__ bank, const int64_t* __restrict__ mem_len,
+                                      const int32_t* __restrict__ head, float* __restrict__ lin, int C, int cap,
+                                      int D) {
+    const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wg >= C * cap) return;
+    const int c = wg / cap, r = wg - c * cap;
+    float* dst = lin + (size_t)wg * D;
+    if (r < (int)mem_len[c]) {
+        const float* src = bank + ((size_t)c * cap + (head[c] + r) % cap) * D;
+        for (int d = lane; d < D; d += 32) dst[d] = src[d];
+    } else {
+        for (int d = lane; d < D; d += 32) dst[d] = 0.f;
+    }
+}
+
+}  // namespace
+
+extern "C" int mgp_mined_gather(const float* xhat_nd, const int32_t* idx, const int64_t* gt, int32_t* top1,
+                               float* rows, int B, int HW, int C, int K, int D, int T, void* stream) {
+    if (!xhat_nd || !idx || !gt || !top1 || !rows) return MGP_ERR_INVALID;
+    if (B <= 0 || HW <= 0 || C <= 0 || K <= 0 || D <= 0 || T <= 0 || (D & 3)) return MGP_ERR_INVALID;
+    const int warps = B * K;
+    mined_gather_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(xhat_nd, idx, gt, top1, rows, B, HW, C, K, D, T);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}
+
+extern "C" int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, uint8_t* updated, const float* rows,
+                                const int32_t* top1, const int64_t* gt, int32_t* plan, int B, int C, int K, int D,
+                                int cap, void* stream) {
+    if (!bank || !mem_len || !head || !updated || !rows || !top1 || !gt || !plan) return MGP_ERR_INVALID;
+    if (B <= 0 || C <= 0 || K <= 0 || D <= 0 || cap <= 0 || (D & 3)) return MGP_ERR_INVALID;
+    if (B > 8192) return MGP_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t smem = (size_t)3 * B * sizeof(int);
+    MGP_CUDA(cudaFuncSetAttribute(enqueue_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    enqueue_plan_kernel<<<1, 1024, smem, st>>>(mem_len, head, updated, top1, gt, plan, B, C, K, cap);
+    MGP_CHECK_LAUNCH();
+    const int warps = B * K;
+    enqueue_scatter_kernel<<<(warps + 7) / 8, 256, 0, st>>>(bank, rows, gt, plan, B, K, D, cap);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}
+
+extern "C" int mgp_bank_linearize(const float* bank, const int64_t* mem_len, const int32_t* head, float* lin, int C,
+                                  int cap, int D, void* stream) {
+    if (!bank || !mem_len || !head || !lin || C <= 0 || cap <= 0 || D <= 0) return MGP_ERR_INVALID;
+    const int warps = C * cap;
+    bank_linearize_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(bank, mem_len, head, lin, C, cap, D);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}

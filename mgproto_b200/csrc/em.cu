@@ -1,0 +1,511 @@
+// a10-a14: memory-bank EM.  ref: model.py:277-301 (update_GMM), :303-321 (_e_step),
+// :338-365 (_m_step), :367-401 (_m_step_diversified), :403-421 (_score).
+//
+// The reference runs, per updated class and EM loop, ~100 small ATen launches plus an autograd
+// backward and an Adam step over the whole [C,K,D] mean tensor (~40k launches per iteration at
+// B=256).  Here one iteration's update_GMM is 2 + 2*num_em_loop + 1 launches, independent of
+// the number of classes, with identical sequential semantics:
+//
+//   em_plan            active[c] = updated[c] && bank full; order[c] = rank among active
+//   em_update phase 0  leading zero-gradient Adam steps of every class
+//   per EM loop:       em_stats  (E-step + segmented weighted reduction over bank rows; HBM-bound)
+//                      [multi-GPU: all-reduce of `stats` here]
+//                      em_update phase 1 (gradient from S0/S1 + diversity term, Adam step, pi momentum)
+//   em_update phase 2  trailing zero-gradient Adam steps
+//
+// Why the zero-gradient steps: the reference's optimiser owns the whole mean tensor, so every
+// (class, loop) step also decays the momentum of -- and moves -- all other classes.
+// Classes only interact through the global step count, so each class replays its own timeline.
+#include "mgp_common.cuh"
+
+namespace {
+
+constexpr float EM_EPS = 1e-10f;
+
+__global__ void __launch_bounds__(1024)
+em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_len, int32_t* __restrict__ order,
+               int32_t* __restrict__ sched, int32_t* __restrict__ adam_step, int step0, int C, int cap, int num_em_loop) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const bool act = updated[c] != 0 && mem_len[c] >= (int64_t)cap;   // ref model.py:283, :289
+        order[c] = act ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int r = 0;
+        for (int c = 0; c < C; ++c) {
+            const int a = order[c];
+            order[c] = a ? r : -1;
+            r += a;
+        }
+        sched[0] = r;
+        const int s0 = adam_step ? adam_step[0] : step0;
+        sched[1] = s0;
+        if (adam_step) adam_step[0] = s0 + r * num_em_loop;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) updated[c] = 0;      // ref model.py:287, :301
+}
+
+// ---------------------------------------------------------------------------------------------
+// E-step for one row held by a warp: lane l owns elements d = 4*(l + 32 j) .. +3, j < VEC4.
+// Returns the log-normaliser; lane k (and k+32) keeps the smoothed responsibility of component k.
+template <int VEC4>
+__device__ __forceinline__ float warp_estep_row(const float4 (&xv)[VEC4], const float* __restrict__ s_mu,
+                                                const float* __restrict__ s_rinv, const float* __restrict__ s_cst,
+                                                int K, int D, int lane, float alpha, float& r_lo, float& r_hi,
+                                                float& lr_lo, float& lr_hi) {
+    float w_lo = -INFINITY, w_hi = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC4; ++j) {
+            const int d = 4 * (lane + 32 * j);
+            if (d >= D) continue;
+            const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + d);
+            const float4 r = *reinterpret_cast<const float4*>(s_rinv + k * D + d);
+            float t;
+            t = (xv[j].x - m.x) * r.x; q = fmaf(t, t, q);
+            t = (xv[j].y - m.y) * r.y; q = fmaf(t, t, q);
+            t = (xv[j].z - m.z) * r.z; q = fmaf(t, t, q);
+            t = (xv[j].w - m.w) * r.w; q = fmaf(t, t, q);
+        }
+        q = warp_sum(q);
+        const float wl = s_cst[k] - 0.5f * q;       // lp + log(pi + eps)   (ref :316)
+        if (lane == (k & 31)) {
+            if (k < 32) w_lo = wl; else w_hi = wl;
+        }
+    }
+    const float mx = warp_max(fmaxf(w_lo, w_hi));
+    const float e_lo = (lane < K) ? expf(w_lo - mx) : 0.f;
+    const float e_hi = (lane + 32 < K) ? expf(w_hi - mx) : 0.f;
+    const float se = warp_sum(e_lo + e_hi);
+    const float norm = mx + logf(se);               // logsumexp (ref :318)
+    lr_lo = w_lo - norm;                            // log_resp (ref :319)
+    lr_hi = w_hi - norm;
+    const float den = 1.0f + (float)K * alpha;      // sum_k (resp + alpha) with sum resp = se/se
+    // the reference normalises by the actual sum of (resp + alpha); resp sums to 1 up to rounding
+    const float rs = warp_sum(((lane < K) ? expf(lr_lo) : 0.f) + ((lane + 32 < K) ? expf(lr_hi) : 0.f));
+    const float den2 = rs + (float)K * alpha;
+    (void)den;
+    r_lo = (lane < K) ? (expf(lr_lo) + alpha) / den2 : 0.f;        // ref :380-383
+    r_hi = (lane + 32 < K) ? (expf(lr_hi) + alpha) / den2 : 0.f;
+    return norm;
+}
+
+constexpr int RB = 32;  // rows per batch
+
+// grid (C, n_split); CTA (c, s) reduces rows [seg_begin, seg_end) of class c.
+// Thread t owns outputs o = t + 256 i (o = k*D + d) of S1 (and S2); threads t < K own S0[t].
+template <int VEC4, int NOUT, bool WITH_S2>
+__global__ void __launch_bounds__(256)
+em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ order, const float* __restrict__ mu,
+                const float* __restrict__ sigma, const float* __restrict__ weight, float alpha, int row_begin,
+                int row_end, int n_split, float* __restrict__ stats, size_t stat_stride, int C, int K, int D, int cap) {
+    const int c = blockIdx.x;
+    if (order[c] < 0) return;
+    extern __shared__ __align__(16) float sm[];
+    float* s_mu = sm;                    // [K][D]
+    float* s_rinv = s_mu + K * D;        // [K][D]
+    float* s_x = s_rinv + K * D;         // [RB][D]
+    float* s_r = s_x + RB * D;           // [RB][K]
+    float* s_cst = s_r + RB * K;         // [K]
+    __shared__ float s_ll[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = C * K;
+    const int split = blockIdx.y;
+    const int rows = row_end - row_begin;
+    const int per = (rows + n_split - 1) / n_split;
+    const int seg_b = row_begin + split * per;
+    const int seg_e = min(row_end, seg_b + per);
+
+    for (int i = tid; i < K * D; i += 256) {
+        s_mu[i] = mu[(size_t)c * K * D + i];
+        s_rinv[i] = 1.0f / (sigma[(size_t)c * K * D + i] + EM_EPS);                 // ref :333
+    }
+    __syncthreads();
+    for (int k = warp; k < K; k += 8) {
+        float ls = 0.f;
+        for (int d = lane; d < D; d += 32) ls += logf(sigma[(size_t)c * K * D + k * D + d] + EM_EPS);   // ref :334
+        ls = warp_sum(ls);
+        if (lane == 0)
+            s_cst[k] = -0.5f * (float)D * MGP_LOG_2PI - ls + logf(weight[(size_t)c * P + c * K + k] + EM_EPS);
+    }
+    __syncthreads();
+
+    float a1[NOUT], a2[NOUT];
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
+    float a0 = 0.f, ll = 0.f;
+    const int KD = K * D;
+
+    for (int r0 = seg_b; r0 < seg_e; r0 += RB) {
+        const int nr = min(RB, seg_e - r0);
+        // phase 1: E-step, warp per row
+        for (int rl = warp; rl < nr; rl += 8) {
+            const float* xr = bank + ((size_t)c * cap + r0 + rl) * D;
+            float4 xv[VEC4];
+#pragma unroll
+            for (int j = 0; j < VEC4; ++j) {
+                xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (4 * (lane + 32 * j) < D) {
+                    xv[j] = __ldg(reinterpret_cast<const float4*>(xr) + lane + 32 * j);
+                    *reinterpret_cast<float4*>(s_x + rl * D + 4 * (lane + 32 * j)) = xv[j];
+                }
+            }
+            float r_lo, r_hi, l_lo, l_hi;
+            const float norm = warp_estep_row<VEC4>(xv, s_mu, s_rinv, s_cst, K, D, lane, alpha, r_lo, r_hi, l_lo, l_hi);
+            if (lane < K) s_r[rl * K + lane] = r_lo;
+            if (lane + 32 < K) s_r[rl * K + lane + 32] = r_hi;
+            if (lane == 0) ll += norm;
+        }
+        __syncthreads();
+        // phase 2: rank-nr update of the statistics, thread per output
+        for (int rl = 0; rl < nr; ++rl) {
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) {
+                const int o = tid + 256 * i;
+                if (o < KD) {
+                    const int k = o / D, d = o - k * D;
+                    const float xx = s_x[rl * D + d];
+                    const float rx = s_r[rl * K + k] * xx;
+                    a1[i] += rx;
+                    if (WITH_S2) a2[i] = fmaf(rx, xx, a2[i]);
+                }
+            }
+            if (tid < K) a0 += s_r[rl * K + tid];
+        }
+        __syncthreads();
+    }
+
+    float* out = stats + ((size_t)c * n_split + split) * stat_stride;
+    if (tid < K) out[tid] = a0;
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) {
+        const int o = tid + 256 * i;
+        if (o < KD) {
+            out[K + o] = a1[i];
+            if (WITH_S2) out[K + KD + o] = a2[i];
+        }
+    }
+    if (lane == 0) s_ll[warp] = ll;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_ll[w];
+        out[stat_stride - 1] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct AdamCfg {
+    float lr, beta1, beta2, eps;
+};
+
+__device__ __forceinline__ void adam_apply(float& p, float& m, float& v, float g, const AdamCfg& a, double b1pow,
+                                           double b2pow) {
+    // torch.optim.Adam (_single_tensor_adam): lerp, mul/addcmul, bias corrections in double
+    m = m + (g - m) * (1.0f - a.beta1);
+    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+    const float step_size = (float)((double)a.lr / (1.0 - b1pow));
+    const float bc2_sqrt = (float)sqrt(1.0 - b2pow);
+    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+    p = p - step_size * (m / denom);
+}
+
+// grid C, block 256.  See the file header for the phases.
+__global__ void __launch_bounds__(256)
+em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_stride, int n_rows_total,
+                 const int32_t* __restrict__ order, const int32_t* __restrict__ sched, float* __restrict__ mu,
+                 const float* __restrict__ sigma, float* __restrict__ weight, float* __restrict__ exp_avg,
+                 float* __restrict__ exp_avg_sq, int em_loop, int num_em_loop, int phase, AdamCfg adam, float tau,
+                 float lamda, float* __restrict__ grad_out, int only_class, int C, int K, int D) {
+    const int c = blockIdx.x;
+    const int ord = order[c];
+    const int n_active = sched[0];
+    const int step0 = sched[1];
+    const int tid = threadIdx.x;
+    const int KD = K * D;
+    const int P = C * K;
+    float* mu_c = mu + (size_t)c * KD;
+    const bool do_adam = (exp_avg != nullptr);
+
+    if (phase != 1) {
+        if (!do_adam) return;
+        int first, count;   // steps first+1 .. first+count are zero-gradient steps of this class
+        if (phase == 0) {
+            first = step0;
+            count = (ord >= 0) ? num_em_loop * ord : num_em_loop * n_active;
+        } else {
+            if (ord < 0) return;
+            first = step0 + num_em_loop * (ord + 1);
+            count = num_em_loop * (n_active - ord - 1);
+        }
+        if (count <= 0) return;
+        for (int o = tid; o < KD; o += 256) {
+            float p = mu_c[o], m = exp_avg[(size_t)c * KD + o], v = exp_avg_sq[(size_t)c * KD + o];
+            double b1p = pow((double)adam.beta1, (double)first), b2p = pow((double)adam.beta2, (double)first);
+            for (int s = 0; s < count; ++s) {
+                b1p *= (double)adam.beta1;
+                b2p *= (double)adam.beta2;
+                adam_apply(p, m, v, 0.f, adam, b1p, b2p);
+            }
+            mu_c[o] = p;
+            exp_avg[(size_t)c * KD + o] = m;
+            exp_avg_sq[(size_t)c * KD + o] = v;
+        }
+        return;
+    }
+
+    // phase 1: one EM-loop step of an active class
+    if (ord < 0) return;
+    if (only_class >= 0 && c != only_class) return;
+    extern __shared__ float sm[];
+    float* s_mu = sm;               // [K][D]
+    float* s_e = s_mu + KD;         // [K][K] exp(-|mu_i - mu_j|^2)
+    float* s_s0 = s_e + K * K;      // [K]
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < KD; i += 256) s_mu[i] = mu_c[i];
+    for (int k = tid; k < K; k += 256) {
+        float t = 0.f;
+        for (int s = 0; s < n_split; ++s) t += stats[((size_t)c * n_split + s) * stat_stride + k];
+        s_s0[k] = t;
+    }
+    __syncthreads();
+    for (int pr = warp; pr < K * K; pr += 8) {      // ref utils/helpers.py:13-14, model.py:390-392
+        const int i = pr / K, j = pr - i * K;
+        float t = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float df = s_mu[i * D + d] - s_mu[j * D + d];
+            t = fmaf(df, df, t);
+        }
+        t = warp_sum(t);
+        if (lane == 0) s_e[pr] = (i == j) ? 0.f : expf(-t);
+    }
+    __syncthreads();
+    const float n_rows = (float)n_rows_total;
+    const float div_scale = -4.0f * lamda / ((float)K * (float)(K - 1));
+    const int step = step0 + num_em_loop * ord + em_loop + 1;
+    const double b1p = pow((double)adam.beta1, (double)step), b2p = pow((double)adam.beta2, (double)step);
+    for (int o = tid; o < KD; o += 256) {
+        const int k = o / D, d = o - k * D;
+        float s1 = 0.f;
+        for (int s = 0; s < n_split; ++s) s1 += stats[((size_t)c * n_split + s) * stat_stride + K + o];
+        const float sg = sigma[(size_t)c * KD + o] + EM_EPS;
+        const float w = 1.0f / (sg * sg);
+        const float muv = s_mu[o];
+        float g = -(s1 - muv * s_s0[k]) * w / n_rows;
+        float esum = 0.f, emu = 0.f;
+        for (int j = 0; j < K; ++j) {
+            const float e = s_e[k * K + j];
+            esum += e;
+            emu = fmaf(e, s_mu[j * D + d], emu);
+        }
+        g += div_scale * (esum * muv - emu);
+        if (grad_out) grad_out[(size_t)c * KD + o] = g;
+        if (do_adam) {
+            float p = muv, m = exp_avg[(size_t)c * KD + o], v = exp_avg_sq[(size_t)c * KD + o];
+            adam_apply(p, m, v, g, adam, b1p, b2p);
+            mu_c[o] = p;
+            exp_avg[(size_t)c * KD + o] = m;
+            exp_avg_sq[(size_t)c * KD + o] = v;
+        }
+    }
+    // pi <- tau*pi + (1-tau)*(S0 + eps)/n   (ref :385, :399, :297-298)
+    for (int k = tid; k < K; k += 256) {
+        float* wp = weight + (size_t)c * P + (size_t)c * K + k;
+        const float pi_new = (s_s0[k] + EM_EPS) / n_rows;
+        *wp = tau * (*wp) + (1.0f - tau) * pi_new;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// E-step on explicit rows (API parity for _e_step / _score).  Warp per row.
+template <int VEC4>
+__global__ void __launch_bounds__(256)
+em_estep_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ sigma,
+                const float* __restrict__ pi, float* __restrict__ log_resp, float* __restrict__ score, int n, int K,
+                int D) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_mu = sm;
+    float* s_rinv = s_mu + K * D;
+    float* s_cst = s_rinv + K * D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < K * D; i += 256) {
+        s_mu[i] = mu[i];
+        s_rinv[i] = 1.0f / (sigma[i] + EM_EPS);
+    }
+    __syncthreads();
+    for (int k = warp; k < K; k += 8) {
+        float ls = 0.f;
+        for (int d = lane; d < D; d += 32) ls += logf(sigma[k * D + d] + EM_EPS);
+        ls = warp_sum(ls);
+        if (lane == 0) s_cst[k] = -0.5f * (float)D * MGP_LOG_2PI - ls + logf(pi[k] + EM_EPS);
+    }
+    __syncthreads();
+    for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
+        float4 xv[VEC4];
+#pragma unroll
+        for (int j = 0; j < VEC4; ++j) {
+            xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * (lane + 32 * j) < D) xv[j] = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * D) + lane + 32 * j);
+        }
+        float r_lo, r_hi, l_lo, l_hi;
+        const float norm = warp_estep_row<VEC4>(xv, s_mu, s_rinv, s_cst, K, D, lane, 0.f, r_lo, r_hi, l_lo, l_hi);
+        if (log_resp) {
+            if (lane < K) log_resp[(size_t)row * K + lane] = l_lo;
+            if (lane + 32 < K) log_resp[(size_t)row * K + lane + 32] = l_hi;
+        }
+        if (score && lane == 0) score[row] = norm;
+    }
+}
+
+// closed-form M-step (ref :338-365): thread per (k,d), serial over rows.
+__global__ void em_mstep_closed_kernel(const float* __restrict__ x, const float* __restrict__ log_resp, float alpha,
+                                       float* __restrict__ pi_out, float* __restrict__ mu_out,
+                                       float* __restrict__ sigma_out, int n, int K, int D) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= K * D) return;
+    const int k = o / D, d = o - k * D;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < n; ++r) {
+        float den = 0.f;
+        for (int j = 0; j < K; ++j) den += expf(log_resp[(size_t)r * K + j]) + alpha;
+        const float rr = (expf(log_resp[(size_t)r * K + k]) + alpha) / den;
+        const float xx = x[(size_t)r * D + d];
+        s0 += rr;
+        s1 = fmaf(rr, xx, s1);
+        s2 = fmaf(rr * xx, xx, s2);
+    }
+    const float pi = s0 + EM_EPS;
+    const float m = s1 / pi;
+    const float x2 = s2 / pi;
+    const float xmu = m * s1 / pi;
+    const float var = x2 - 2.0f * xmu + m * m + EM_EPS;
+    mu_out[o] = m;
+    sigma_out[o] = sqrtf(var);
+    if (d == 0) pi_out[k] = pi / (float)n;
+}
+
+}  // namespace
+
+extern "C" size_t mgp_em_stat_stride(int K, int D, int with_s2) {
+    return (size_t)K + (size_t)K * D * (with_s2 ? 2 : 1) + 1;
+}
+
+extern "C" int mgp_em_plan(uint8_t* updated, const int64_t* mem_len, int32_t* order, int32_t* sched,
+                           int32_t* adam_step, int step0, int C, int cap, int num_em_loop, void* stream) {
+    if (!updated || !mem_len || !order || !sched || C <= 0 || cap <= 0 || num_em_loop <= 0) return MGP_ERR_INVALID;
+    em_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(updated, mem_len, order, sched, adam_step, step0, C, cap,
+                                                         num_em_loop);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}
+
+template <int VEC4, bool S2>
+static int launch_stats(int nout, dim3 grid, size_t smem, cudaStream_t st, const float* bank, const int32_t* order,
+                        const float* mu, const float* sigma, const float* weight, float alpha, int rb, int re,
+                        int n_split, float* stats, size_t stride, int C, int K, int D, int cap) {
+#define MGP_EM_CASE(NO)                                                                                             \
+    if (nout <= NO) {                                                                                               \
+        MGP_CUDA(cudaFuncSetAttribute(em_stats_kernel<VEC4, NO, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)smem));                                                                  \
+        em_stats_kernel<VEC4, NO, S2><<<grid, 256, smem, st>>>(bank, order, mu, sigma, weight, alpha, rb, re,       \
+                                                               n_split, stats, stride, C, K, D, cap);               \
+        MGP_CHECK_LAUNCH();                                                                                         \
+        return MGP_OK;                                                                                              \
+    }
+    MGP_EM_CASE(2)
+    MGP_EM_CASE(5)
+    MGP_EM_CASE(10)
+    MGP_EM_CASE(20)
+    MGP_EM_CASE(40)
+    MGP_EM_CASE(80)
+#undef MGP_EM_CASE
+    return MGP_ERR_UNSUPPORTED;
+}
+
+extern "C" int mgp_em_stats(const float* bank, const int32_t* order, const float* mu, const float* sigma,
+                            const float* weight_cp, float alpha, int row_begin, int row_end, int n_split, int with_s2,
+                            float* stats, int C, int K, int D, int cap, void* stream) {
+    if (!bank || !order || !mu || !sigma || !weight_cp || !stats) return MGP_ERR_INVALID;
+    if (C <= 0 || K <= 0 || D <= 0 || cap <= 0 || n_split <= 0 || row_begin < 0 || row_end > cap || row_begin >= row_end)
+        return MGP_ERR_INVALID;
+    if (K > 64 || (D % 4) != 0 || D > 512) return MGP_ERR_UNSUPPORTED;
+    const size_t stride = mgp_em_stat_stride(K, D, with_s2);
+    const int nout = (K * D + 255) / 256;
+    const size_t smem = ((size_t)2 * K * D + (size_t)RB * D + (size_t)RB * K + K) * sizeof(float);
+    if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
+    dim3 grid(C, n_split);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vec4 = (D + 127) / 128;
+#define MGP_EM_V(V)                                                                                                 \
+    if (vec4 == V)                                                                                                  \
+        return with_s2 ? launch_stats<V, true>(nout, grid, smem, st, bank, order, mu, sigma, weight_cp, alpha,      \
+                                               row_begin, row_end, n_split, stats, stride, C, K, D, cap)            \
+                       : launch_stats<V, false>(nout, grid, smem, st, bank, order, mu, sigma, weight_cp, alpha,     \
+                                                row_begin, row_end, n_split, stats, stride, C, K, D, cap);
+    MGP_EM_V(1)
+    MGP_EM_V(2)
+    MGP_EM_V(3)
+    MGP_EM_V(4)
+#undef MGP_EM_V
+    return MGP_ERR_UNSUPPORTED;
+}
+
+extern "C" int mgp_em_update(const float* stats, int n_split, int with_s2, int n_rows_total, const int32_t* order,
+                             const int32_t* sched, float* mu, const float* sigma, float* weight_cp, float* exp_avg,
+                             float* exp_avg_sq, int em_loop, int num_em_loop, int phase, float lr, float beta1,
+                             float beta2, float adam_eps, float tau, float lamda, float* grad_out, int only_class,
+                             int C, int K, int D, void* stream) {
+    if (!order || !sched || !mu || !sigma || !weight_cp) return MGP_ERR_INVALID;
+    if (phase < 0 || phase > 2 || C <= 0 || K <= 0 || D <= 0 || num_em_loop <= 0) return MGP_ERR_INVALID;
+    if (phase == 1 && (!stats || n_split <= 0 || n_rows_total <= 0)) return MGP_ERR_INVALID;
+    if ((exp_avg == nullptr) != (exp_avg_sq == nullptr)) return MGP_ERR_INVALID;
+    const size_t stride = mgp_em_stat_stride(K, D, with_s2);
+    const size_t smem = ((size_t)K * D + (size_t)K * K + K) * sizeof(float);
+    if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
+    MGP_CUDA(cudaFuncSetAttribute(em_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AdamCfg a{lr, beta1, beta2, adam_eps};
+    em_update_kernel<<<C, 256, smem, (cudaStream_t)stream>>>(stats, n_split, stride, n_rows_total, order, sched, mu,
+                                                             sigma, weight_cp, exp_avg, exp_avg_sq, em_loop,
+                                                             num_em_loop, phase, a, tau, lamda, grad_out, only_class,
+                                                             C, K, D);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}
+
+extern "C" int mgp_em_estep(const float* x, const float* mu, const float* sigma, const float* pi, float* log_resp,
+                            float* score, int n, int K, int D, void* stream) {
+    if (!x || !mu || !sigma || !pi || n <= 0 || K <= 0 || D <= 0) return MGP_ERR_INVALID;
+    if (K > 64 || (D % 4) != 0 || D > 512) return MGP_ERR_UNSUPPORTED;
+    const size_t smem = ((size_t)2 * K * D + K) * sizeof(float);
+    if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
+    int grid = (n + 7) / 8;
+    if (grid > 148 * 8) grid = 148 * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+#define MGP_ES(V)                                                                                                   \
+    if ((D + 127) / 128 == V) {                                                                                           \
+        MGP_CUDA(cudaFuncSetAttribute(em_estep_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        em_estep_kernel<V><<<grid, 256, smem, st>>>(x, mu, sigma, pi, log_resp, score, n, K, D);                    \
+        MGP_CHECK_LAUNCH();                                                                                         \
+        return MGP_OK;                                                                                              \
+    }
+    MGP_ES(1)
+    MGP_ES(2)
+    MGP_ES(3)
+    MGP_ES(4)
+#undef MGP_ES
+    return MGP_ERR_UNSUPPORTED;
+}
+
+extern "C" int mgp_em_mstep_closed(const float* x, const float* log_resp, float alpha, float* pi_out, float* mu_out,
+                                   float* sigma_out, int n, int K, int D, void* stream) {
+    if (!x || !log_resp || !pi_out || !mu_out || !sigma_out || n <= 0 || K <= 0 || D <= 0) return MGP_ERR_INVALID;
+    const int tot = K * D;
+    em_mstep_closed_kernel<<<(tot + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, log_resp, alpha, pi_out, mu_out,
+                                                                                sigma_out, n, K, D);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}

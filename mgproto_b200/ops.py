@@ -1,0 +1,295 @@
+"""Tensor-level wrappers over the C ABI (include/mgproto_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every function validates its
+tensors (CUDA, fp32, contiguous) and enqueues hand-written sm_100a kernels on the current
+stream through ctypes.  Nothing falls back to ATen or to the CPU.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_OUT_LOGP_BPHW, MGP_OUT_LOGP_NP,
+                   MGP_OUT_NEGP_BPHW, check)
+
+__all__ = ["normalize_fwd", "logprob", "head_select", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
+           "bank_linearize", "em_plan", "em_stats", "em_update", "em_estep", "em_mstep_closed", "push_argmin",
+           "MATH_MODES"]
+
+MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO}
+
+_launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int):
+    global _launches
+    _launches += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("mgproto_b200: %s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("mgproto_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("mgproto_b200: %s must be contiguous" % name)
+    return t
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _math(math) -> int:
+    return MATH_MODES[math] if isinstance(math, str) else int(math)
+
+
+# ----------------------------------------------------------------------------------- a1
+def normalize_fwd(x_bdhw: torch.Tensor, want_nchw: bool = False):
+    """ref model.py:210-211.  -> (xhat [N,D], inv_norm [N], xhat_nchw [B,D,H,W] | None)."""
+    x = _req(x_bdhw, torch.float32, "x")
+    B, D, H, W = x.shape
+    HW = H * W
+    xhat = torch.empty((B * HW, D), device=x.device, dtype=torch.float32)
+    inv = torch.empty((B * HW,), device=x.device, dtype=torch.float32)
+    nchw = torch.empty_like(x) if want_nchw else None
+    lib = _lib.load()
+    check(lib.mgp_normalize_fwd(x.data_ptr(), xhat.data_ptr(), inv.data_ptr(), _p(nchw), B, D, HW, _stream()),
+          "mgp_normalize_fwd")
+    _count(1)
+    return xhat, inv, nchw
+
+
+# ----------------------------------------------------------------------------------- a2/a3/a16
+def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, eps=0.0, eps_log=0.0,
+            math="auto"):
+    """ref model.py:256-275 / :323-336.  xhat [N,D], mu/sigma [P,D] ->
+    layout NP: [N,P] log p;  BPHW: [B,P,HW] log p;  NEGP: [B,P,HW] -exp(log p)."""
+    x = _req(xhat_nd, torch.float32, "xhat")
+    mu = _req(mu_pd, torch.float32, "mu")
+    sg = _req(sigma_pd, torch.float32, "sigma")
+    N, D = x.shape
+    P = mu.shape[0]
+    if mu.shape != (P, D) or sg.shape != (P, D):
+        raise RuntimeError("mgproto_b200: mu/sigma must be [P, D]")
+    if layout == MGP_OUT_LOGP_NP:
+        B_, HW_ = N, 1
+        out = torch.empty((N, P), device=x.device, dtype=torch.float32)
+    else:
+        if B is None or HW is None or B * HW != N:
+            raise RuntimeError("mgproto_b200: BPHW layouts need B*HW == N")
+        B_, HW_ = B, HW
+        out = torch.empty((B, P, HW), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    m = _math(math)
+    nbytes = lib.mgp_logprob_ws_bytes(P, D, m)
+    ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
+    check(lib.mgp_logprob_fwd(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), float(eps), float(eps_log), out.data_ptr(),
+                              int(layout), B_, HW_, P, D, m, ws.data_ptr(), nbytes, _stream()), "mgp_logprob_fwd")
+    _count(2)
+    return out
+
+
+# ----------------------------------------------------------------------------------- a4-a7
+def head_select(logp_bphw, weight_cp, gt, T, C, K):
+    """ref model.py:188-206, :218-222, :254 -> (logits [B,C,T], vals [B,P,T], idx [B,P,T] int32)."""
+    lp = _req(logp_bphw, torch.float32, "logp")
+    w = _req(weight_cp, torch.float32, "last_layer.weight")
+    B, P, HW = lp.shape
+    if P != C * K or w.shape != (C, P):
+        raise RuntimeError("mgproto_b200: shape mismatch in head_select")
+    if gt is not None:
+        gt = _req(gt, torch.int64, "gt")
+        if gt.shape != (B,):
+            raise RuntimeError("mgproto_b200: gt must be [B]")
+    logits = torch.empty((B, C, T), device=lp.device, dtype=torch.float32)
+    vals = torch.empty((B, P, T), device=lp.device, dtype=torch.float32)
+    idx = torch.empty((B, P, T), device=lp.device, dtype=torch.int32)
+    check(_lib.load().mgp_head_select(lp.data_ptr(), w.data_ptr(), _p(gt), logits.data_ptr(), vals.data_ptr(),
+                                      idx.data_ptr(), B, HW, C, K, T, _stream()), "mgp_head_select")
+    _count(1)
+    return logits, vals, idx
+
+
+class HeadFunction(torch.autograd.Function):
+    """features [B,D,H,W] -> log mixture evidences [B,C,T] (ref model.py:210-222, :254).
+
+    Forward = normalise + log-likelihood + top-T + pi-mix, all in the CUDA library.  Backward
+    differentiates w.r.t. the features only (mu/sigma are detached in the reference,
+    model.py:264-265; last_layer.weight has requires_grad=False) by re-differentiating the T
+    selected patches per (image, prototype) instead of saving the N*P*D autograd tape.
+    Also returns (non-differentiable) xhat [N,D] and idx [B,P,T] for the bank enqueue.
+    """
+
+    @staticmethod
+    def forward(ctx, x_add, mu_ckd, sigma_ckd, weight_cp, gt, T, math):
+        C, K, D = mu_ckd.shape
+        B, _, H, W = x_add.shape
+        HW = H * W
+        x_add = x_add.contiguous()
+        mu = mu_ckd.detach().reshape(C * K, D).contiguous()
+        sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
+        wt = weight_cp.detach().contiguous()
+        xhat, inv, _ = normalize_fwd(x_add)
+        lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)
+        logits, vals, idx = head_select(lp, wt, gt, T, C, K)
+        ctx.save_for_backward(logits, vals, idx, wt, gt if gt is not None else torch.empty(0), xhat, inv, mu, sg)
+        ctx.has_gt = gt is not None
+        ctx.dims = (B, HW, C, K, D, T, H, W)
+        ctx.mark_non_differentiable(xhat, idx)
+        return logits, xhat, idx
+
+    @staticmethod
+    def backward(ctx, g_logits, _g_xhat, _g_idx):
+        logits, vals, idx, wt, gt, xhat, inv, mu, sg = ctx.saved_tensors
+        B, HW, C, K, D, T, H, W = ctx.dims
+        g = _req(g_logits.contiguous(), torch.float32, "grad_logits")
+        lib = _lib.load()
+        nbytes = lib.mgp_head_bwd_ws_bytes(B, HW, C * K, D)
+        ws = torch.empty((nbytes,), device=g.device, dtype=torch.uint8)
+        gx = torch.empty((B, D, H, W), device=g.device, dtype=torch.float32)
+        check(lib.mgp_head_bwd(g.data_ptr(), logits.data_ptr(), vals.data_ptr(), idx.data_ptr(), wt.data_ptr(),
+                               gt.data_ptr() if ctx.has_gt else 0, xhat.data_ptr(), inv.data_ptr(), mu.data_ptr(),
+                               sg.data_ptr(), ws.data_ptr(), nbytes, gx.data_ptr(), B, HW, C, K, D, T, _stream()),
+              "mgp_head_bwd")
+        _count(3)
+        return gx, None, None, None, None, None, None
+
+
+def head_forward(x_add, mu_ckd, sigma_ckd, weight_cp, gt, T, math="auto"):
+    return HeadFunction.apply(x_add, mu_ckd, sigma_ckd, weight_cp, gt, int(T), math)
+
+
+# ----------------------------------------------------------------------------------- a8/a9
+def mined_gather(xhat_nd, idx, gt, HW, C, K):
+    """ref model.py:225-226: (top1 [B,K] int32, rows [B,K,D]) of every image's GT-class prototypes."""
+    _req(xhat_nd, torch.float32, "xhat")
+    _req(idx, torch.int32, "idx")
+    _req(gt, torch.int64, "gt")
+    B, P, T = idx.shape
+    D = xhat_nd.shape[1]
+    top1 = torch.empty((B, K), device=idx.device, dtype=torch.int32)
+    rows = torch.empty((B, K, D), device=idx.device, dtype=torch.float32)
+    check(_lib.load().mgp_mined_gather(xhat_nd.data_ptr(), idx.data_ptr(), gt.data_ptr(), top1.data_ptr(),
+                                       rows.data_ptr(), B, HW, C, K, D, T, _stream()), "mgp_mined_gather")
+    _count(1)
+    return top1, rows
+
+
+def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt):
+    """ref model.py:228-250 + utils/memory.py:31-73, in place on (bank, mem_len, head, updated)."""
+    bank = _req(bank, torch.float32, "bank")
+    C, cap, D = bank.shape
+    B, K = top1.shape
+    _req(mem_len, torch.int64, "mem_len")
+    _req(head, torch.int32, "head")
+    _req(updated, torch.uint8, "updated")
+    _req(rows, torch.float32, "rows")
+    _req(top1, torch.int32, "top1")
+    _req(gt, torch.int64, "gt")
+    if rows.shape != (B, K, D) or gt.shape != (B,):
+        raise RuntimeError("mgproto_b200: enqueue shape mismatch")
+    plan = torch.empty((B * K,), device=bank.device, dtype=torch.int32)
+    check(_lib.load().mgp_bank_enqueue(bank.data_ptr(), mem_len.data_ptr(), head.data_ptr(), updated.data_ptr(),
+                                       rows.data_ptr(), top1.data_ptr(), gt.data_ptr(), plan.data_ptr(), B, C, K, D,
+                                       cap, _stream()), "mgp_bank_enqueue")
+    _count(2)
+
+
+def bank_linearize(bank, mem_len, head):
+    bank = _req(bank, torch.float32, "bank")
+    C, cap, D = bank.shape
+    lin = torch.empty_like(bank)
+    check(_lib.load().mgp_bank_linearize(bank.data_ptr(), mem_len.data_ptr(), head.data_ptr(), lin.data_ptr(), C, cap,
+                                         D, _stream()), "mgp_bank_linearize")
+    _count(1)
+    return lin
+
+
+# ----------------------------------------------------------------------------------- a10-a14
+def em_stat_stride(K, D, with_s2=False) -> int:
+    return int(_lib.load().mgp_em_stat_stride(K, D, 1 if with_s2 else 0))
+
+
+def em_plan(updated, mem_len, order, sched, step0, cap, num_em_loop, adam_step=None):
+    C = updated.numel()
+    check(_lib.load().mgp_em_plan(updated.data_ptr(), mem_len.data_ptr(), order.data_ptr(), sched.data_ptr(),
+                                  _p(adam_step), int(step0), C, int(cap), int(num_em_loop), _stream()), "mgp_em_plan")
+    _count(1)
+
+
+def em_stats(bank, order, mu_ckd, sigma_ckd, weight_cp, alpha, stats, n_split, row_begin=0, row_end=None,
+             with_s2=False):
+    C, cap, D = bank.shape
+    K = mu_ckd.shape[1]
+    if row_end is None:
+        row_end = cap
+    check(_lib.load().mgp_em_stats(bank.data_ptr(), order.data_ptr(), mu_ckd.data_ptr(), sigma_ckd.data_ptr(),
+                                   weight_cp.data_ptr(), float(alpha), int(row_begin), int(row_end), int(n_split),
+                                   1 if with_s2 else 0, stats.data_ptr(), C, K, D, cap, _stream()), "mgp_em_stats")
+    _count(1)
+
+
+def em_update(stats, n_split, n_rows_total, order, sched, mu_ckd, sigma_ckd, weight_cp, exp_avg, exp_avg_sq, em_loop,
+              num_em_loop, phase, lr, beta1, beta2, adam_eps, tau, lamda=1.0, grad_out=None, only_class=-1,
+              with_s2=False):
+    C, K, D = mu_ckd.shape
+    check(_lib.load().mgp_em_update(_p(stats), int(n_split), 1 if with_s2 else 0, int(n_rows_total), order.data_ptr(),
+                                    sched.data_ptr(), mu_ckd.data_ptr(), sigma_ckd.data_ptr(), weight_cp.data_ptr(),
+                                    _p(exp_avg), _p(exp_avg_sq), int(em_loop), int(num_em_loop), int(phase), float(lr),
+                                    float(beta1), float(beta2), float(adam_eps), float(tau), float(lamda),
+                                    _p(grad_out), int(only_class), C, K, D, _stream()), "mgp_em_update")
+    _count(1)
+
+
+def em_estep(x_nd, mu_kd, sigma_kd, pi_k, want_log_resp=True, want_score=True):
+    """ref model.py:303-321 / :403-421 -> (log_resp [n,K] | None, score [n] | None)."""
+    x = _req(x_nd.contiguous(), torch.float32, "x")
+    mu = _req(mu_kd.contiguous(), torch.float32, "mu")
+    sg = _req(sigma_kd.contiguous(), torch.float32, "sigma")
+    pi = _req(pi_k.contiguous(), torch.float32, "pi")
+    n, D = x.shape
+    K = mu.shape[0]
+    lr = torch.empty((n, K), device=x.device, dtype=torch.float32) if want_log_resp else None
+    sc = torch.empty((n,), device=x.device, dtype=torch.float32) if want_score else None
+    check(_lib.load().mgp_em_estep(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), pi.data_ptr(), _p(lr), _p(sc), n, K, D,
+                                   _stream()), "mgp_em_estep")
+    _count(1)
+    return lr, sc
+
+
+def em_mstep_closed(x_nd, log_resp_nk, alpha):
+    """ref model.py:338-365 -> (pi [K], mu [K,D], sigma [K,D])."""
+    x = _req(x_nd.contiguous(), torch.float32, "x")
+    lr = _req(log_resp_nk.contiguous(), torch.float32, "log_resp")
+    n, D = x.shape
+    K = lr.shape[1]
+    pi = torch.empty((K,), device=x.device, dtype=torch.float32)
+    mu = torch.empty((K, D), device=x.device, dtype=torch.float32)
+    sg = torch.empty((K, D), device=x.device, dtype=torch.float32)
+    check(_lib.load().mgp_em_mstep_closed(x.data_ptr(), lr.data_ptr(), float(alpha), pi.data_ptr(), mu.data_ptr(),
+                                          sg.data_ptr(), n, K, D, _stream()), "mgp_em_mstep_closed")
+    _count(1)
+    return pi, mu, sg
+
+
+# ----------------------------------------------------------------------------------- f1
+def push_argmin(logp_bphw, labels, C, K):
+    """ref push.py:125-158 -> (arg [B,K] int32 flat HW index, val [B,K] = -p at the argmin)."""
+    lp = _req(logp_bphw, torch.float32, "logp")
+    lab = _req(labels, torch.int64, "labels")
+    B, P, HW = lp.shape
+    arg = torch.empty((B, K), device=lp.device, dtype=torch.int32)
+    val = torch.empty((B, K), device=lp.device, dtype=torch.float32)
+    check(_lib.load().mgp_push_argmin(lp.data_ptr(), lab.data_ptr(), arg.data_ptr(), val.data_ptr(), B, HW, C, K,
+                                      _stream()), "mgp_push_argmin")
+    _count(1)
+    return arg, val

@@ -68,8 +68,9 @@ int mgp_normalize_bwd(const float* g_xhat_nd, const float* xhat_nd, const float*
  * `eps` is added to sigma inside the quotient; `eps_log` inside the logarithm
  * (compute_log_prob: 0 / 0, _estimate_log_prob: 1e-10 / 1e-10).
  * xhat_nd [N,D] (N = B*HW; for MGP_OUT_LOGP_NP pass B = N, HW = 1 if there is no image
- * structure), mu/sigma [P,D]; `ws` is scratch of at least mgp_logprob_ws_bytes(P, D, math). */
-size_t mgp_logprob_ws_bytes(int P, int D, int math);
+ * structure), mu/sigma [P,D]; `ws` is scratch of at least mgp_logprob_ws_bytes(B, HW, P, D, math)
+ * bytes (the tensor-core path stages fp16 hi/lo operands there). */
+size_t mgp_logprob_ws_bytes(int B, int HW, int P, int D, int math);
 int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const float* sigma, float eps,
                     float eps_log, float* out, int out_layout, int B, int HW, int P, int D,
                     int math, void* ws, size_t ws_bytes, void* stream);

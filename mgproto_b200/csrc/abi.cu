@@ -5,7 +5,7 @@ int mgp_logprob_simt_launch(const float* xhat, const float* mu, const float* sig
                             float* out, int layout, int B, int HW, int P, int D, float* ws, cudaStream_t st);
 // logprob_tc.cu
 bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D);
-size_t mgp_logprob_tc_ws_bytes(int P, int D);
+size_t mgp_logprob_tc_ws_bytes(long long N, int P, int D);
 int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log,
                           float* out, int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes,
                           cudaStream_t st);
@@ -32,15 +32,15 @@ extern "C" int mgp_has_tensor_core_path(void) {
 #endif
 }
 
-extern "C" size_t mgp_logprob_ws_bytes(int P, int D, int math) {
+extern "C" size_t mgp_logprob_ws_bytes(int B, int HW, int P, int D, int math) {
     size_t simt = ((size_t)P * D + P) * sizeof(float);
 #ifdef MGP_WITH_TC
-    if (math != MGP_MATH_FP32) {
-        size_t tc = mgp_logprob_tc_ws_bytes(P, D);
+    if (math != MGP_MATH_FP32 && mgp_logprob_tc_supported(0, B, HW, P, D)) {
+        size_t tc = mgp_logprob_tc_ws_bytes((long long)B * HW, P, D);
         return tc > simt ? tc : simt;
     }
 #endif
-    (void)math;
+    (void)math; (void)B; (void)HW;
     return simt;
 }
 
@@ -54,7 +54,7 @@ extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const floa
         !mgp_aligned16(ws))
         return MGP_ERR_INVALID;
     if ((long long)B * HW > 0x7fffffffLL) return MGP_ERR_UNSUPPORTED;
-    if (ws_bytes < mgp_logprob_ws_bytes(P, D, math)) return MGP_ERR_WORKSPACE;
+    if (ws_bytes < mgp_logprob_ws_bytes(B, HW, P, D, math)) return MGP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
 #ifdef MGP_WITH_TC
     if (math == MGP_MATH_TC || math == MGP_MATH_AUTO) {

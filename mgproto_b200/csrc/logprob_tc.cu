@@ -1,2 +1,540 @@
-// placeholder until the tcgen05 kernel lands (built only with -DMGP_WITH_TC)
+// a2/a16 on the 5th-gen tensor cores (MGP_MATH_TC): the squared Mahalanobis distance as a GEMM
+//
+//   q[n,p] = sum_d w_pd x_nd^2 - 2 sum_d (w mu)_pd x_nd + sum_d w_pd mu_pd^2 ,   w = 1/(sigma+eps)^2
+//          = [x^2 | x]_n . [w | -2 w mu]_p + c2_p                       (inner dim 2D, general diagonal)
+//          = w_p |x_n|^2 + x_n . (-2 w mu)_p + c2_p                     (inner dim  D, sigma constant over d:
+//                                                                        every state the shipped loop reaches)
+//   log p = e0_p + e1_p * acc[n,p] + e2_p * |x_n|^2
+//
+// Precision: operands are split into fp16 hi + lo (22 mantissa bits) and accumulated as
+// hi*hi + lo*hi + hi*lo in fp32 TMEM accumulators -- three kind::f16 passes instead of one TF32
+// pass at half rate; |error| on q ~1e-6, inside the 1e-4 bar on logits (a single bf16 or tf32
+// pass is not).  Power-of-two scalings keep the lo parts in fp16's normal range and are undone
+// exactly in the epilogue.
+//
+// Structure (one persistent CTA per SM, 8 warps):
+//   warp 0   TMA producer: prototype (A) K-blocks through an S-stage mbarrier ring; the x tile (B,
+//            128 patches x Kg) once per n-tile, resident in shared memory
+//   warp 1   one thread issues tcgen05.mma (M=128 prototypes x N=128 patches x K=16), 2 TMEM accumulators
+//   warp 2   TMEM allocator
+//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, affine fix-up, stores.  TMEM lane = prototype,
+//            column = patch, so for the [N,P] layout the 32 lanes of a warp write 32 consecutive floats
+//            of one output row -- fully coalesced straight from registers, no staging pass.
+// HBM traffic per launch: 4*N*P (output) + 8*N*Kg (fp16 hi/lo operand written by the prep pass and
+// read once) + 4*N*D (x) -- the output dominates; the kernel is bound by the HBM write stream.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "mgp_common.cuh"
+
+namespace {
+
+constexpr int NT = 128;          // patches per tile  (UMMA N)
+constexpr int PT = 128;          // prototypes per tile (UMMA M)
+constexpr int KB = 64;           // K elements per smem block (128 B rows, SWIZZLE_128B)
+constexpr int SUB_BYTES = 128 * KB * 2;   // one [128 x 64] fp16 block = 16 KiB
+constexpr float X_SCALE = 256.0f;
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0; !ok; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && (it & 1023u) == 1023u) {              // a protocol bug must fault, not hang the device
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// start>>4 | LBO(16 B)=1 <<16 | SBO(1024 B)=64 <<32 | version 1 <<46 | layout SWIZZLE_128B(2) <<61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(PT >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------ prep
+// Prototype side: Bh/Bl [P, 2D] fp16 = split of scale_p * [ w | -2 w mu ]; e0,e1,e2 [P]; noniso flag.
+__global__ void tc_proto_prep_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, float eps,
+                                     float eps_log, __half* __restrict__ bh, __half* __restrict__ bl,
+                                     float* __restrict__ e0, float* __restrict__ e1, float* __restrict__ e2,
+                                     int* __restrict__ noniso, int P, int D) {
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    const float* mr = mu + (size_t)p * D;
+    const float* sr = sigma + (size_t)p * D;
+    const float s0 = sr[0];
+    float ls = 0.f, c2 = 0.f, mx = 0.f;
+    bool same = true;
+    for (int d = lane; d < D; d += 32) {
+        const float s = sr[d];
+        same = same && (s == s0);
+        const float r = 1.0f / (s + eps);
+        const float w = r * r;
+        const float m = mr[d];
+        ls += logf(s + eps_log);
+        c2 = fmaf(w * m, m, c2);
+        mx = fmaxf(mx, fmaxf(w, fabsf(2.0f * w * m)));
+    }
+    ls = warp_sum(ls);
+    c2 = warp_sum(c2);
+    mx = warp_max(mx);
+    same = __all_sync(0xffffffffu, same);
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);                       // mx = f * 2^ex, f in [0.5, 1)
+    const float scale = ldexpf(1.0f, 8 - ex);            // max |B'| * scale in [128, 256)
+    for (int d = lane; d < D; d += 32) {
+        const float r = 1.0f / (sr[d] + eps);
+        const float w = r * r;
+        const float v0 = w * scale, v1 = -2.0f * w * mr[d] * scale;
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        bh[(size_t)p * 2 * D + d] = h0;
+        bl[(size_t)p * 2 * D + d] = __float2half_rn(v0 - __half2float(h0));
+        bh[(size_t)p * 2 * D + D + d] = h1;
+        bl[(size_t)p * 2 * D + D + d] = __float2half_rn(v1 - __half2float(h1));
+    }
+    if (lane == 0) {
+        const float r0 = 1.0f / (s0 + eps);
+        e0[p] = -0.5f * (float)D * MGP_LOG_2PI - ls - 0.5f * c2;
+        e1[p] = -0.5f / (scale * X_SCALE);
+        e2[p] = -0.5f * r0 * r0;                          // used only when every prototype is isotropic
+        if (!same) atomicOr(noniso, 1);
+    }
+}
+
+// Patch side: Ah/Al [N, 2D] fp16 = split of 256 * [ x^2 | x ] (the x^2 half only if some prototype is
+// anisotropic), sn [N] = |x|^2.  Warp per row.
+__global__ void tc_x_prep_kernel(const float* __restrict__ x, __half* __restrict__ ah, __half* __restrict__ al,
+                                 float* __restrict__ sn, const int* __restrict__ noniso, int N, int D) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const bool gen = (*noniso != 0);
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)n * D);
+    __half* hr = ah + (size_t)n * 2 * D;
+    __half* lr = al + (size_t)n * 2 * D;
+    float ss = 0.f;
+    for (int d4 = lane; d4 < D / 4; d4 += 32) {
+        const float4 v = __ldg(xr + d4);
+        const float a[4] = {v.x, v.y, v.z, v.w};
+        __align__(8) __half h[4], l[4], h2[4], l2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ss = fmaf(a[i], a[i], ss);
+            const float s1 = a[i] * X_SCALE;
+            h[i] = __float2half_rn(s1);
+            l[i] = __float2half_rn(s1 - __half2float(h[i]));
+            const float s2 = a[i] * a[i] * X_SCALE;
+            h2[i] = __float2half_rn(s2);
+            l2[i] = __float2half_rn(s2 - __half2float(h2[i]));
+        }
+        *reinterpret_cast<uint2*>(hr + D + d4 * 4) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(lr + D + d4 * 4) = *reinterpret_cast<uint2*>(l);
+        if (gen) {
+            *reinterpret_cast<uint2*>(hr + d4 * 4) = *reinterpret_cast<uint2*>(h2);
+            *reinterpret_cast<uint2*>(lr + d4 * 4) = *reinterpret_cast<uint2*>(l2);
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) sn[n] = ss;
+}
+
+// ------------------------------------------------------------------------------------------ main
+struct TcParams {
+    const float* e0;
+    const float* e1;
+    const float* e2;
+    const float* sn;
+    const int* noniso;
+    float* out;
+    int N, HW, P, D;
+    int n_ntiles, n_ptiles, ppu, n_pgroups, n_units;
+    int stages;
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256, 1)
+logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                  const __grid_constant__ CUtensorMap map_ph, const __grid_constant__ CUtensorMap map_pl,
+                  const TcParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024 B alignment
+    uint8_t* base_ptr = smem_raw + (base - raw);
+
+    const bool gen = (*prm.noniso != 0);
+    const int nkb = (gen ? 2 * prm.D : prm.D) / KB;               // K blocks per tile
+    const int kcol0 = gen ? 0 : prm.D;                            // isotropic: only the [x] / [-2 w mu] half
+    const int S = prm.stages;
+
+    // carve-up: x tile (hi blocks, lo blocks) | S stages of (proto hi, proto lo) | barriers | sn tile
+    const int x_blocks = 2 * (2 * prm.D / KB);                    // sized for the general case
+    const uint32_t x_base = base;
+    const uint32_t st_base = x_base + (uint32_t)x_blocks * SUB_BYTES;
+    const uint32_t misc = st_base + (uint32_t)S * 2 * SUB_BYTES;
+    uint8_t* misc_ptr = base_ptr + (misc - base);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc_ptr);       // full[S] empty[S] x_full x_empty tfull[2] tempty[2]
+    const uint32_t bar0 = misc;
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
+    const uint32_t X_FULL = bar0 + 8u * (2 * S), X_EMPTY = X_FULL + 8u;
+    auto TFULL = [&](int a) { return X_EMPTY + 8u + 8u * a; };
+    auto TEMPTY = [&](int a) { return X_EMPTY + 24u + 8u * a; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
+    float* s_sn = reinterpret_cast<float*>(bars + 2 * S + 8);     // [NT]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(X_FULL, 1);
+        mbar_init(X_EMPTY, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // contiguous range of work units for this CTA; unit = (n-tile, group of `ppu` prototype tiles)
+    const int u_begin = (int)(((long long)prm.n_units * blockIdx.x) / gridDim.x);
+    const int u_end = (int)(((long long)prm.n_units * (blockIdx.x + 1)) / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        // =========================== TMA producer ===========================
+        int stage = 0;
+        uint32_t phase = 0, xe_par = 0;
+        int cur_nt = -1;
+        for (int u = u_begin; u < u_end; ++u) {
+            const int nt = u / prm.n_pgroups, pg = u - nt * prm.n_pgroups;
+            if (nt != cur_nt) {
+                if (cur_nt >= 0) { mbar_wait(X_EMPTY, xe_par); xe_par ^= 1u; }
+                mbar_expect_tx(X_FULL, (uint32_t)(2 * nkb) * SUB_BYTES);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tma_load_2d(x_base + (uint32_t)kb * SUB_BYTES, &map_xh, kcol0 + kb * KB, nt * NT, X_FULL);
+                    tma_load_2d(x_base + (uint32_t)(nkb + kb) * SUB_BYTES, &map_xl, kcol0 + kb * KB, nt * NT, X_FULL);
+                }
+                cur_nt = nt;
+            }
+            const int pt_end = min(prm.n_ptiles, (pg + 1) * prm.ppu);
+            for (int pt = pg * prm.ppu; pt < pt_end; ++pt) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(EMPTY(stage), phase ^ 1u);
+                    mbar_expect_tx(FULL(stage), 2 * SUB_BYTES);
+                    const uint32_t dst = st_base + (uint32_t)stage * 2 * SUB_BYTES;
+                    tma_load_2d(dst, &map_ph, kcol0 + kb * KB, pt * PT, FULL(stage));
+                    tma_load_2d(dst + SUB_BYTES, &map_pl, kcol0 + kb * KB, pt * PT, FULL(stage));
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // =========================== MMA issuer ===========================
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_par = 0, xf_par = 0;
+        int cur_nt = -1;
+        for (int u = u_begin; u < u_end; ++u) {
+            const int nt = u / prm.n_pgroups, pg = u - nt * prm.n_pgroups;
+            if (nt != cur_nt) {
+                mbar_wait(X_FULL, xf_par);
+                xf_par ^= 1u;
+                cur_nt = nt;
+            }
+            const int pt_end = min(prm.n_ptiles, (pg + 1) * prm.ppu);
+            for (int pt = pg * prm.ppu; pt < pt_end; ++pt) {
+                mbar_wait(TEMPTY(acc), acc_par ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * NT;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(FULL(stage), phase);
+                    tc_fence_after();
+                    const uint32_t ph = st_base + (uint32_t)stage * 2 * SUB_BYTES, pl = ph + SUB_BYTES;
+                    const uint32_t xh = x_base + (uint32_t)kb * SUB_BYTES, xl = x_base + (uint32_t)(nkb + kb) * SUB_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KB / 16; ++k) {
+                        const uint32_t off = (uint32_t)k * 32u;   // 16 fp16 = 32 B inside the 128 B swizzle row
+                        const uint64_t a_h = umma_desc(ph + off), a_l = umma_desc(pl + off);
+                        const uint64_t b_h = umma_desc(xh + off), b_l = umma_desc(xl + off);
+                        tc_mma_f16(d_tmem, a_h, b_h, IDESC, (kb | k) != 0);
+                        tc_mma_f16(d_tmem, a_l, b_h, IDESC, 1u);
+                        tc_mma_f16(d_tmem, a_h, b_l, IDESC, 1u);
+                    }
+                    tc_commit(EMPTY(stage));                      // frees the stage when these MMAs retire
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(TFULL(acc));                            // accumulator ready for the epilogue
+                acc ^= 1;
+                if (acc == 0) acc_par ^= 1u;
+            }
+            const int next_nt = (u + 1 < u_end) ? (u + 1) / prm.n_pgroups : -1;
+            if (next_nt != cur_nt) tc_commit(X_EMPTY);            // x tile may be overwritten
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue ===========================
+        const int q = warp - 4;                                   // TMEM lane quarter of this warp
+        const int et = q * 32 + lane;                             // lane (= prototype row) within the tile
+        int acc = 0;
+        uint32_t acc_par = 0;
+        int cur_nt = -1;
+        const int N = prm.N, P = prm.P, HW = prm.HW;
+        for (int u = u_begin; u < u_end; ++u) {
+            const int nt = u / prm.n_pgroups, pg = u - nt * prm.n_pgroups;
+            if (nt != cur_nt) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int n = nt * NT + et;
+                s_sn[et] = (n < N) ? prm.sn[n] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_nt = nt;
+            }
+            const int pt_end = min(prm.n_ptiles, (pg + 1) * prm.ppu);
+            for (int pt = pg * prm.ppu; pt < pt_end; ++pt) {
+                const int p = pt * PT + et;
+                const bool pok = p < P;
+                const float c0 = pok ? __ldg(prm.e0 + p) : 0.f;
+                const float c1 = pok ? __ldg(prm.e1 + p) : 0.f;
+                const float c2 = (pok && !gen) ? __ldg(prm.e2 + p) : 0.f;
+                mbar_wait(TFULL(acc), acc_par);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < NT / 32; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + ch * 32), r);
+                    tmem_ld_wait();
+                    const int n0 = nt * NT + ch * 32;
+                    if (LAYOUT == MGP_OUT_LOGP_NP) {
+                        float* dst = prm.out + (size_t)n0 * P + p;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = fmaf(c1, __uint_as_float(r[j]), fmaf(c2, s_sn[ch * 32 + j], c0));
+                            if (pok && n0 + j < N) dst[(size_t)j * P] = v;
+                        }
+                    } else {
+                        int b = n0 / HW, hw = n0 - b * HW;
+                        const bool vec = ((HW & 3) == 0);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float v[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float lp = fmaf(c1, __uint_as_float(r[j + i]), fmaf(c2, s_sn[ch * 32 + j + i], c0));
+                                v[i] = (LAYOUT == MGP_OUT_NEGP_BPHW) ? -expf(lp) : lp;
+                            }
+                            if (pok) {
+                                if (vec && n0 + j + 3 < N) {
+                                    *reinterpret_cast<float4*>(prm.out + ((size_t)b * P + p) * HW + hw) =
+                                        make_float4(v[0], v[1], v[2], v[3]);
+                                } else {
+                                    int bb = b, hh = hw;
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        if (n0 + j + i < N) prm.out[((size_t)bb * P + p) * HW + hh] = v[i];
+                                        if (++hh == HW) { hh = 0; ++bb; }
+                                    }
+                                }
+                            }
+                            hw += 4;
+                            while (hw >= HW) { hw -= HW; ++b; }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(TEMPTY(acc));
+                acc ^= 1;
+                if (acc == 0) acc_par ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// [rows, cols] fp16 row-major, box = 64 cols x 128 rows, 128 B swizzle; OOB rows read as zero
+bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(__half)};
+    cuuint32_t box[2] = {KB, 128};
+    cuuint32_t es[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct WsLayout {
+    size_t bh, bl, e0, e1, e2, flag, ah, al, sn, total;
+};
+WsLayout ws_layout(long long N, int P, int D) {
+    WsLayout w;
+    size_t o = 0;
+    w.bh = o; o = align256(o + (size_t)P * 2 * D * 2);
+    w.bl = o; o = align256(o + (size_t)P * 2 * D * 2);
+    w.e0 = o; o = align256(o + (size_t)P * 4);
+    w.e1 = o; o = align256(o + (size_t)P * 4);
+    w.e2 = o; o = align256(o + (size_t)P * 4);
+    w.flag = o; o = align256(o + 4);
+    w.ah = o; o = align256(o + (size_t)N * 2 * D * 2);
+    w.al = o; o = align256(o + (size_t)N * 2 * D * 2);
+    w.sn = o; o = align256(o + (size_t)N * 4);
+    w.total = o;
+    return w;
+}
+
+}  // namespace
+
+bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D) {
+    (void)layout;
+    if (D != 64 && D != 128) return false;                  // K blocks of 64; x tile resident (general: 2D wide)
+    if ((long long)B * HW < 1 || P < 1) return false;
+    return get_encode() != nullptr;
+}
+
+size_t mgp_logprob_tc_ws_bytes(long long N, int P, int D) { return ws_layout(N, P, D).total; }
+
+int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log, float* out,
+                          int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const long long N = (long long)B * HW;
+    const WsLayout w = ws_layout(N, P, D);
+    if (ws_bytes < w.total) return MGP_ERR_WORKSPACE;
+    uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+    __half* bh = reinterpret_cast<__half*>(wsb + w.bh);
+    __half* bl = reinterpret_cast<__half*>(wsb + w.bl);
+    __half* ah = reinterpret_cast<__half*>(wsb + w.ah);
+    __half* al = reinterpret_cast<__half*>(wsb + w.al);
+    float* e0 = reinterpret_cast<float*>(wsb + w.e0);
+    float* e1 = reinterpret_cast<float*>(wsb + w.e1);
+    float* e2 = reinterpret_cast<float*>(wsb + w.e2);
+    float* sn = reinterpret_cast<float*>(wsb + w.sn);
+    int* flag = reinterpret_cast<int*>(wsb + w.flag);
+
+    MGP_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    tc_proto_prep_kernel<<<(P + 7) / 8, 256, 0, st>>>(mu, sigma, eps, eps_log, bh, bl, e0, e1, e2, flag, P, D);
+    MGP_CHECK_LAUNCH();
+    tc_x_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(xhat, ah, al, sn, flag, (int)N, D);
+    MGP_CHECK_LAUNCH();
+
+    CUtensorMap mxh, mxl, mph, mpl;
+    if (!make_map(&mxh, ah, (uint64_t)N, 2 * D) || !make_map(&mxl, al, (uint64_t)N, 2 * D) ||
+        !make_map(&mph, bh, (uint64_t)P, 2 * D) || !make_map(&mpl, bl, (uint64_t)P, 2 * D))
+        return MGP_ERR_UNSUPPORTED;
+
+    TcParams prm;
+    prm.e0 = e0; prm.e1 = e1; prm.e2 = e2; prm.sn = sn; prm.noniso = flag; prm.out = out;
+    prm.N = (int)N; prm.HW = HW; prm.P = P; prm.D = D;
+    prm.n_ntiles = (int)((N + NT - 1) / NT);
+    prm.n_ptiles = (P + PT - 1) / PT;
+    int dev = 0, sms = 148;
+    MGP_CUDA(cudaGetDevice(&dev));
+    MGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // split the prototype tiles of an n-tile into groups so that there are >= ~8 units per CTA
+    int ppu = prm.n_ptiles;
+    while (ppu > 1 && (long long)prm.n_ntiles * ((prm.n_ptiles + ppu - 1) / ppu) < 8LL * sms) ppu = (ppu + 1) / 2;
+    prm.ppu = ppu;
+    prm.n_pgroups = (prm.n_ptiles + ppu - 1) / ppu;
+    prm.n_units = prm.n_ntiles * prm.n_pgroups;
+    const int x_blocks = 2 * (2 * D / KB);
+    const size_t fixed = (size_t)x_blocks * SUB_BYTES + 1024 /*align*/ + 1024 /*barriers + sn*/;
+    int stages = (int)((227 * 1024 - fixed) / (2 * SUB_BYTES));
+    if (stages > 6) stages = 6;
+    if (stages < 2) return MGP_ERR_UNSUPPORTED;
+    prm.stages = stages;
+    const size_t smem = fixed + (size_t)stages * 2 * SUB_BYTES;
+    const int grid = prm.n_units < sms ? prm.n_units : sms;
+
+#define MGP_TC_LAUNCH(L)                                                                                           \
+    do {                                                                                                           \
+        MGP_CUDA(cudaFuncSetAttribute(logprob_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        logprob_tc_kernel<L><<<grid, 256, smem, st>>>(mxh, mxl, mph, mpl, prm);                                     \
+    } while (0)
+    if (layout == MGP_OUT_LOGP_NP) MGP_TC_LAUNCH(MGP_OUT_LOGP_NP);
+    else if (layout == MGP_OUT_LOGP_BPHW) MGP_TC_LAUNCH(MGP_OUT_LOGP_BPHW);
+    else MGP_TC_LAUNCH(MGP_OUT_NEGP_BPHW);
+#undef MGP_TC_LAUNCH
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}

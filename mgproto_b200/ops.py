@@ -90,11 +90,11 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
         out = torch.empty((B, P, HW), device=x.device, dtype=torch.float32)
     lib = _lib.load()
     m = _math(math)
-    nbytes = lib.mgp_logprob_ws_bytes(P, D, m)
+    nbytes = lib.mgp_logprob_ws_bytes(B_, HW_, P, D, m)
     ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
     check(lib.mgp_logprob_fwd(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), float(eps), float(eps_log), out.data_ptr(),
                               int(layout), B_, HW_, P, D, m, ws.data_ptr(), nbytes, _stream()), "mgp_logprob_fwd")
-    _count(2)
+    _count(4 if nbytes > (P * D + P) * 4 else 2)
     return out
 
 

@@ -307,3 +307,52 @@ def test_state_dict_roundtrip(golden):
     sd2 = net2.state_dict()
     for k in sd:
         assert torch.equal(sd[k].cpu(), sd2[k].cpu()), k
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core log-likelihood kernel (tcgen05, fp16 hi/lo x3) against the exact fp32 SIMT kernel
+# and a float64 restatement, at shapes with ragged tiles and at the BASELINE size
+@pytest.mark.parametrize("sigma_mode", ["iso", "diag"])
+@pytest.mark.parametrize("shape", [(3, 49, 130, 64), (5, 196, 2000, 128), (2, 200, 257, 128)])
+def test_logprob_tc_vs_fp32(shape, sigma_mode):
+    from mgproto_b200 import ops, _lib
+    if not _lib.load().mgp_has_tensor_core_path():
+        pytest.skip("library built without the tcgen05 path")
+    B, HW, P, D = shape
+    g = torch.Generator().manual_seed(5)
+    x = F.normalize(torch.randn(B * HW, D, generator=g), dim=1).to(_dev())
+    mu = F.normalize(torch.rand(P, D, generator=g), dim=1).to(_dev())
+    if sigma_mode == "iso":
+        sg = (0.25 + 0.5 * torch.rand(P, 1, generator=g)).expand(P, D).contiguous().to(_dev())
+    else:
+        sg = (0.2 + 0.6 * torch.rand(P, D, generator=g)).to(_dev())
+    ref64 = (-0.5 * D * np.log(2 * np.pi) - sg.double().log().sum(1)[None, :]
+             - 0.5 * (((x.double()[:, None, :] - mu.double()[None]) / sg.double()[None]) ** 2).sum(-1))
+    for layout in (0, 1, 2):
+        a = ops.logprob(x, mu, sg, layout, B=B, HW=HW, math="tc")
+        b = ops.logprob(x, mu, sg, layout, B=B, HW=HW, math="fp32")
+        r = ref64 if layout == 0 else ref64.view(B, HW, P).permute(0, 2, 1)
+        if layout == 2:
+            r = -r.exp()
+        torch.testing.assert_close(a.double(), r, rtol=2e-5, atol=2e-5 if layout != 2 else 1e-12)
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 if layout != 2 else 1e-12)
+
+
+def test_logprob_tc_baseline_size_properties():
+    """cfg2 size (B=256, P=2000, D=128): KA1 identity on a strided sample + exact agreement of the
+    three output layouts with each other (size-independent properties; no CPU oracle at this size)."""
+    from mgproto_b200 import ops, _lib
+    if not _lib.load().mgp_has_tensor_core_path():
+        pytest.skip("library built without the tcgen05 path")
+    B, HW, P, D = 256, 196, 2000, 128
+    g = torch.Generator().manual_seed(1)
+    x = F.normalize(torch.randn(B * HW, D, generator=g), dim=1).to(_dev())
+    mu = F.normalize(torch.rand(P, D, generator=g), dim=1).to(_dev())
+    sg = torch.full((P, D), 1 / np.sqrt(2 * np.pi), device=_dev())
+    lp = ops.logprob(x, mu, sg, 0, math="tc")
+    rows = torch.arange(0, B * HW, 97, device=_dev())
+    ref = -np.pi * ((x[rows].double()[:, None, :] - mu.double()[None]) ** 2).sum(-1)       # KA1
+    torch.testing.assert_close(lp[rows].double(), ref, rtol=1e-5, atol=2e-5)
+    lp_b = ops.logprob(x, mu, sg, 1, B=B, HW=HW, math="tc")
+    assert torch.equal(lp_b, lp.view(B, HW, P).permute(0, 2, 1).contiguous())
+    assert torch.isfinite(lp).all()

@@ -13,23 +13,25 @@
 // exactly in the epilogue.
 //
 // Structure (one persistent CTA per SM, 8 warps):
-//   warp 0   TMA producer: prototype (A) K-blocks through an S-stage mbarrier ring; the x tile (B,
-//            128 patches x Kg) once per n-tile, resident in shared memory
+//   warp 0   TMA producer: prototype (A) K-blocks through an S-stage mbarrier ring
+//   warp 3   TMA producer of the x tile (B, 128 patches x Kg), resident per n-tile, double-buffered when
+//            sigma is isotropic so the next n-tile is prefetched under the current one's MMAs
 //   warp 1   one thread issues tcgen05.mma (M=128 prototypes x N=128 patches x K=16), 2 TMEM accumulators
 //   warp 2   TMEM allocator
-//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, affine fix-up, stores.  TMEM lane = prototype,
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns, affine fix-up, stores.  TMEM lane = prototype,
 //            column = patch, so for the [N,P] layout the 32 lanes of a warp write 32 consecutive floats
 //            of one output row -- fully coalesced straight from registers, no staging pass.
 // HBM traffic per launch: 4*N*P (output) + 8*N*Kg (fp16 hi/lo operand written by the prep pass and
 // read once) + 4*N*D (x) -- the output dominates; the kernel is bound by the HBM write stream.
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "mgp_common.cuh"
 
 namespace {
 
-constexpr int NT = 128;          // patches per tile  (UMMA N)
+constexpr int NT_MAX = 256;      // patches per tile (UMMA N): 256 when sigma is isotropic, else 128
 constexpr int PT = 128;          // prototypes per tile (UMMA M)
 constexpr int KB = 64;           // K elements per smem block (128 B rows, SWIZZLE_128B)
 constexpr int SUB_BYTES = 128 * KB * 2;   // one [128 x 64] fp16 block = 16 KiB
@@ -71,6 +73,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map): operands are stored in global memory
+// already tiled and 128B-swizzled exactly as the UMMA descriptors read them, so a whole 16/32 KiB block
+// is one contiguous transfer.
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// byte offset of element (row r < 128, col k < 64) inside a [128 x 64] fp16 block, K-major SWIZZLE_128B:
+// 8-row groups of 1024 B, 16-byte chunks XOR-ed with the row index
+__host__ __device__ __forceinline__ uint32_t swz_off(int r, int k) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -104,7 +119,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(PT >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n_tile) {
+    return (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(PT >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------ prep
 // Prototype side: Bh/Bl [P, 2D] fp16 = split of scale_p * [ w | -2 w mu ]; e0,e1,e2 [P]; noniso flag.
@@ -202,12 +219,103 @@ struct TcParams {
     const int* noniso;
     float* out;
     int N, HW, P, D;
-    int n_ntiles, n_ptiles, ppu, n_pgroups, n_units;
-    int stages;
+    int n_ptiles, stages;
+    int debug;   // ablation switches for profiling (MGP_TC_DEBUG): 1 no global stores, 2 no TMEM loads, 4 no MMAs
+    // schedule for [0] the general (NT=128) and [1] the isotropic (NT=256) variant; picked on the device by the flag
+    int n_ntiles[2], ppu[2], n_pgroups[2], n_units[2];
 };
 
+constexpr int TC_THREADS = 384;   // warps: 0 proto TMA, 1 MMA, 2 TMEM alloc, 3 x-tile TMA, 4..11 epilogue
+
 template <int LAYOUT>
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const float* __restrict__ s_sn_c, float c0,
+                                               float c1, float c2, int n0, int p, bool pok, const TcParams& prm) {
+    const int N = prm.N, P = prm.P, HW = prm.HW;
+    float v[32];
+    const float4* s4 = reinterpret_cast<const float4*>(s_sn_c);    // |x_n|^2 of the 32 columns (shared memory)
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 s = s4[j4];
+        v[4 * j4 + 0] = fmaf(c1, __uint_as_float(r[4 * j4 + 0]), fmaf(c2, s.x, c0));
+        v[4 * j4 + 1] = fmaf(c1, __uint_as_float(r[4 * j4 + 1]), fmaf(c2, s.y, c0));
+        v[4 * j4 + 2] = fmaf(c1, __uint_as_float(r[4 * j4 + 2]), fmaf(c2, s.z, c0));
+        v[4 * j4 + 3] = fmaf(c1, __uint_as_float(r[4 * j4 + 3]), fmaf(c2, s.w, c0));
+    }
+    if (LAYOUT == MGP_OUT_LOGP_NP && (P & 3) == 0) {
+        // Transpose 4x4 blocks inside each lane quad (4 shuffles per block) so that a thread owns 4
+        // CONSECUTIVE prototypes of one patch row: 8 x STG.128 per thread instead of 32 x STG.32, and a
+        // warp instruction covers 4 rows x 128 B.  (Measured on B200: 8 warps/SM of coalesced STG.32
+        // sustain 3.0 TB/s, the same pattern as STG.128 5.5 TB/s -- tools/micro/store_bw.cu.)
+        const int lane = threadIdx.x & 31;
+        const int l = lane & 3;
+        const bool t1 = (l & 1) != 0, t2 = (l & 2) != 0;
+        const int pq = p - l;                                 // first prototype of the quad
+        const bool qok = pq + 3 < P;                          // P % 4 == 0: a quad is valid or not as a whole
+        float* row = prm.out + (size_t)(n0 + l) * P + pq;
+        const size_t step = (size_t)4 * P;
+        const bool dbg_nostore = (prm.debug & 1) != 0;
+        float sink = 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const float a0 = v[4 * m], a1 = v[4 * m + 1], a2 = v[4 * m + 2], a3 = v[4 * m + 3];
+            const float r0 = __shfl_xor_sync(0xffffffffu, t1 ? a0 : a1, 1);
+            const float r1 = __shfl_xor_sync(0xffffffffu, t1 ? a2 : a3, 1);
+            // column (0+t1) and column (2+t1), each as (even row, odd row) of the lane pair
+            const float c01e = t1 ? r0 : a0, c01o = t1 ? a1 : r0;
+            const float c23e = t1 ? r1 : a2, c23o = t1 ? a3 : r1;
+            const float ze = __shfl_xor_sync(0xffffffffu, t2 ? c01e : c23e, 2);
+            const float zo = __shfl_xor_sync(0xffffffffu, t2 ? c01o : c23o, 2);
+            const float ke = t2 ? c23e : c01e, ko = t2 ? c23o : c01o;
+            const float4 b = t2 ? make_float4(ze, zo, ke, ko) : make_float4(ke, ko, ze, zo);
+            if (dbg_nostore) { sink += b.x + b.y + b.z + b.w; continue; }
+            if (qok && n0 + 4 * m + l < N) *reinterpret_cast<float4*>(row + (size_t)m * step) = b;
+        }
+        if (dbg_nostore && sink == 123.456f) prm.out[0] = sink;
+        return;
+    }
+    if (!pok) return;
+    if (prm.debug & 1) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += v[j];
+        if (acc == 123.456f) prm.out[0] = acc;
+        return;
+    }
+    const bool full = (n0 + 32 <= N);
+    if (LAYOUT == MGP_OUT_LOGP_NP) {
+        float* dst = prm.out + (size_t)n0 * P + p;          // lanes = consecutive p: 128 B per warp store
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[(size_t)j * P] = v[j];
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (n0 + j < N) dst[(size_t)j * P] = v[j];
+        }
+    } else {
+        if (LAYOUT == MGP_OUT_NEGP_BPHW) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = -expf(v[j]);
+        }
+        int b = n0 / HW, hw = n0 - b * HW;
+        if (full && (HW & 3) == 0) {                         // 4 consecutive patches share an image, 16 B aligned
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                *reinterpret_cast<float4*>(prm.out + ((size_t)b * P + p) * HW + hw) =
+                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                hw += 4;
+                if (hw >= HW) { hw -= HW; ++b; }
+            }
+        } else {
+            for (int j = 0; j < 32; ++j) {
+                if (n0 + j < N) prm.out[((size_t)b * P + p) * HW + hw] = v[j];
+                if (++hw == HW) { hw = 0; ++b; }
+            }
+        }
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                   const __grid_constant__ CUtensorMap map_ph, const __grid_constant__ CUtensorMap map_pl,
                   const TcParams prm) {
@@ -217,37 +325,41 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     uint8_t* base_ptr = smem_raw + (base - raw);
 
     const bool gen = (*prm.noniso != 0);
+    const int var = gen ? 0 : 1;
+    const int NT = gen ? 128 : 256;                               // same x-tile bytes either way: NT * Kg * 4
     const int nkb = (gen ? 2 * prm.D : prm.D) / KB;               // K blocks per tile
     const int kcol0 = gen ? 0 : prm.D;                            // isotropic: only the [x] / [-2 w mu] half
     const int S = prm.stages;
+    const int n_pgroups = prm.n_pgroups[var], ppu = prm.ppu[var], n_units = prm.n_units[var];
+    const uint32_t xsub = (uint32_t)NT * KB * 2;                  // one [NT x 64] fp16 block of the x tile
+    const uint32_t idesc = make_idesc(NT);
 
-    // carve-up: x tile (hi blocks, lo blocks) | S stages of (proto hi, proto lo) | barriers | sn tile
-    const int x_blocks = 2 * (2 * prm.D / KB);                    // sized for the general case
+    // carve-up: x tile (1024*D bytes) | S stages of (proto hi, proto lo) | barriers
     const uint32_t x_base = base;
-    const uint32_t st_base = x_base + (uint32_t)x_blocks * SUB_BYTES;
+    const uint32_t st_base = x_base + 1024u * (uint32_t)prm.D;
     const uint32_t misc = st_base + (uint32_t)S * 2 * SUB_BYTES;
     uint8_t* misc_ptr = base_ptr + (misc - base);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(misc_ptr);       // full[S] empty[S] x_full x_empty tfull[2] tempty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc_ptr);       // full[S] empty[S] xfull xempty tfull[2] tempty[2]
     const uint32_t bar0 = misc;
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
-    const uint32_t X_FULL = bar0 + 8u * (2 * S), X_EMPTY = X_FULL + 8u;
-    auto TFULL = [&](int a) { return X_EMPTY + 8u + 8u * a; };
-    auto TEMPTY = [&](int a) { return X_EMPTY + 24u + 8u * a; };
+    const uint32_t XFULL = bar0 + 8u * (2 * S), XEMPTY = bar0 + 8u * (2 * S + 1);
+    auto TFULL = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * S + 4 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
-    float* s_sn = reinterpret_cast<float*>(bars + 2 * S + 8);     // [NT]
+    float* s_sn = reinterpret_cast<float*>(bars + 2 * S + 8);     // [NT_MAX] |x|^2 of the current n-tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        mbar_init(X_FULL, 1);
-        mbar_init(X_EMPTY, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
+        mbar_init(XFULL, 1);
+        mbar_init(XEMPTY, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -256,29 +368,35 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     // contiguous range of work units for this CTA; unit = (n-tile, group of `ppu` prototype tiles)
-    const int u_begin = (int)(((long long)prm.n_units * blockIdx.x) / gridDim.x);
-    const int u_end = (int)(((long long)prm.n_units * (blockIdx.x + 1)) / gridDim.x);
+    const int u_begin = (int)(((long long)n_units * blockIdx.x) / gridDim.x);
+    const int u_end = (int)(((long long)n_units * (blockIdx.x + 1)) / gridDim.x);
 
-    if (warp == 0 && lane == 0) {
-        // =========================== TMA producer ===========================
-        int stage = 0;
-        uint32_t phase = 0, xe_par = 0;
-        int cur_nt = -1;
-        for (int u = u_begin; u < u_end; ++u) {
-            const int nt = u / prm.n_pgroups, pg = u - nt * prm.n_pgroups;
-            if (nt != cur_nt) {
-                if (cur_nt >= 0) { mbar_wait(X_EMPTY, xe_par); xe_par ^= 1u; }
-                mbar_expect_tx(X_FULL, (uint32_t)(2 * nkb) * SUB_BYTES);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    tma_load_2d(x_base + (uint32_t)kb * SUB_BYTES, &map_xh, kcol0 + kb * KB, nt * NT, X_FULL);
-                    tma_load_2d(x_base + (uint32_t)(nkb + kb) * SUB_BYTES, &map_xl, kcol0 + kb * KB, nt * NT, X_FULL);
-                }
-                cur_nt = nt;
+    if (warp == 3 && lane == 0) {
+        // =========================== x-tile TMA producer ===========================
+        if (u_begin < u_end) {
+            const int nt_first = u_begin / n_pgroups, nt_last = (u_end - 1) / n_pgroups;
+            for (int nt = nt_first, c = 0; nt <= nt_last; ++nt, ++c) {
+                if (c >= 1) mbar_wait(XEMPTY, (uint32_t)((c - 1) & 1));
+                mbar_expect_tx(XFULL, (uint32_t)(2 * nkb) * xsub);
+                for (int kb = 0; kb < nkb; ++kb)
+                    for (int r = 0; r < NT; r += 128) {           // TMA box = 128 rows
+                        const uint32_t ro = (uint32_t)r * KB * 2;
+                        tma_load_2d(x_base + (uint32_t)kb * xsub + ro, &map_xh, kcol0 + kb * KB, nt * NT + r, XFULL);
+                        tma_load_2d(x_base + (uint32_t)(nkb + kb) * xsub + ro, &map_xl, kcol0 + kb * KB, nt * NT + r, XFULL);
+                    }
             }
-            const int pt_end = min(prm.n_ptiles, (pg + 1) * prm.ppu);
-            for (int pt = pg * prm.ppu; pt < pt_end; ++pt) {
+        }
+    } else if (warp == 0 && lane == 0) {
+        // =========================== prototype TMA producer ===========================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            const int pg = u % n_pgroups;
+            const int pt_end = min(prm.n_ptiles, (pg + 1) * ppu);
+            for (int pt = pg * ppu; pt < pt_end; ++pt) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(EMPTY(stage), phase ^ 1u);
+                    if (prm.debug & 16) { mbar_arrive(FULL(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
                     mbar_expect_tx(FULL(stage), 2 * SUB_BYTES);
                     const uint32_t dst = st_base + (uint32_t)stage * 2 * SUB_BYTES;
                     tma_load_2d(dst, &map_ph, kcol0 + kb * KB, pt * PT, FULL(stage));
@@ -290,33 +408,34 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     } else if (warp == 1 && lane == 0) {
         // =========================== MMA issuer ===========================
         int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_par = 0, xf_par = 0;
-        int cur_nt = -1;
+        uint32_t phase = 0, acc_par = 0;
+        int cur_nt = -1, c = -1;
         for (int u = u_begin; u < u_end; ++u) {
-            const int nt = u / prm.n_pgroups, pg = u - nt * prm.n_pgroups;
+            const int nt = u / n_pgroups, pg = u - nt * n_pgroups;
             if (nt != cur_nt) {
-                mbar_wait(X_FULL, xf_par);
-                xf_par ^= 1u;
+                ++c;
+                mbar_wait(XFULL, (uint32_t)(c & 1));
                 cur_nt = nt;
             }
-            const int pt_end = min(prm.n_ptiles, (pg + 1) * prm.ppu);
-            for (int pt = pg * prm.ppu; pt < pt_end; ++pt) {
+            const int pt_end = min(prm.n_ptiles, (pg + 1) * ppu);
+            for (int pt = pg * ppu; pt < pt_end; ++pt) {
                 mbar_wait(TEMPTY(acc), acc_par ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * NT;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(FULL(stage), phase);
                     tc_fence_after();
                     const uint32_t ph = st_base + (uint32_t)stage * 2 * SUB_BYTES, pl = ph + SUB_BYTES;
-                    const uint32_t xh = x_base + (uint32_t)kb * SUB_BYTES, xl = x_base + (uint32_t)(nkb + kb) * SUB_BYTES;
+                    const uint32_t xh = x_base + (uint32_t)kb * xsub, xl = x_base + (uint32_t)(nkb + kb) * xsub;
 #pragma unroll
                     for (int k = 0; k < KB / 16; ++k) {
                         const uint32_t off = (uint32_t)k * 32u;   // 16 fp16 = 32 B inside the 128 B swizzle row
                         const uint64_t a_h = umma_desc(ph + off), a_l = umma_desc(pl + off);
                         const uint64_t b_h = umma_desc(xh + off), b_l = umma_desc(xl + off);
-                        tc_mma_f16(d_tmem, a_h, b_h, IDESC, (kb | k) != 0);
-                        tc_mma_f16(d_tmem, a_l, b_h, IDESC, 1u);
-                        tc_mma_f16(d_tmem, a_h, b_l, IDESC, 1u);
+                        if (prm.debug & 4) continue;
+                        tc_mma_f16(d_tmem, a_h, b_h, idesc, (kb | k) != 0);
+                        tc_mma_f16(d_tmem, a_l, b_h, idesc, 1u);
+                        tc_mma_f16(d_tmem, a_h, b_l, idesc, 1u);
                     }
                     tc_commit(EMPTY(stage));                      // frees the stage when these MMAs retire
                     if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -325,80 +444,73 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                 acc ^= 1;
                 if (acc == 0) acc_par ^= 1u;
             }
-            const int next_nt = (u + 1 < u_end) ? (u + 1) / prm.n_pgroups : -1;
-            if (next_nt != cur_nt) tc_commit(X_EMPTY);            // x tile may be overwritten
+            const int next_nt = (u + 1 < u_end) ? (u + 1) / n_pgroups : -1;
+            if (next_nt != cur_nt) tc_commit(XEMPTY);             // x tile may be refilled
         }
     } else if (warp >= 4) {
         // =========================== epilogue ===========================
-        const int q = warp - 4;                                   // TMEM lane quarter of this warp
-        const int et = q * 32 + lane;                             // lane (= prototype row) within the tile
+        // 8 warps drain each accumulator together: warp = (TMEM lane quarter q, column half h).  Inside a
+        // warp the tcgen05.ld of the next 32 columns is in flight while the current 32 are stored.
+        const int e = warp - 4;
+        const int q = e & 3, h = e >> 2;
+        const int et = q * 32 + lane;                             // prototype row within the tile (TMEM lane)
+        const int hcols = NT / 2, nch = hcols / 32;               // 2 (NT=128) or 4 (NT=256) chunks per warp
         int acc = 0;
         uint32_t acc_par = 0;
         int cur_nt = -1;
-        const int N = prm.N, P = prm.P, HW = prm.HW;
+        const bool skip_epi = (prm.debug & 8) != 0;
         for (int u = u_begin; u < u_end; ++u) {
-            const int nt = u / prm.n_pgroups, pg = u - nt * prm.n_pgroups;
+            const int nt = u / n_pgroups, pg = u - nt * n_pgroups;
+            const int pt_end = min(prm.n_ptiles, (pg + 1) * ppu);
+            const int nbase = nt * NT + h * hcols;
+            const float* sn_g = s_sn + h * hcols;
             if (nt != cur_nt) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int n = nt * NT + et;
-                s_sn[et] = (n < N) ? prm.sn[n] : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int i = e * 32 + lane; i < NT; i += 256) {
+                    const int n = nt * NT + i;
+                    s_sn[i] = (n < prm.N) ? prm.sn[n] : 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_nt = nt;
             }
-            const int pt_end = min(prm.n_ptiles, (pg + 1) * prm.ppu);
-            for (int pt = pg * prm.ppu; pt < pt_end; ++pt) {
+            for (int pt = pg * ppu; pt < pt_end; ++pt) {
                 const int p = pt * PT + et;
-                const bool pok = p < P;
+                const bool pok = p < prm.P;
                 const float c0 = pok ? __ldg(prm.e0 + p) : 0.f;
                 const float c1 = pok ? __ldg(prm.e1 + p) : 0.f;
                 const float c2 = (pok && !gen) ? __ldg(prm.e2 + p) : 0.f;
                 mbar_wait(TFULL(acc), acc_par);
                 tc_fence_after();
-#pragma unroll 1
-                for (int ch = 0; ch < NT / 32; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + ch * 32), r);
-                    tmem_ld_wait();
-                    const int n0 = nt * NT + ch * 32;
-                    if (LAYOUT == MGP_OUT_LOGP_NP) {
-                        float* dst = prm.out + (size_t)n0 * P + p;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = fmaf(c1, __uint_as_float(r[j]), fmaf(c2, s_sn[ch * 32 + j], c0));
-                            if (pok && n0 + j < N) dst[(size_t)j * P] = v;
-                        }
-                    } else {
-                        int b = n0 / HW, hw = n0 - b * HW;
-                        const bool vec = ((HW & 3) == 0);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float v[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float lp = fmaf(c1, __uint_as_float(r[j + i]), fmaf(c2, s_sn[ch * 32 + j + i], c0));
-                                v[i] = (LAYOUT == MGP_OUT_NEGP_BPHW) ? -expf(lp) : lp;
-                            }
-                            if (pok) {
-                                if (vec && n0 + j + 3 < N) {
-                                    *reinterpret_cast<float4*>(prm.out + ((size_t)b * P + p) * HW + hw) =
-                                        make_float4(v[0], v[1], v[2], v[3]);
-                                } else {
-                                    int bb = b, hh = hw;
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        if (n0 + j + i < N) prm.out[((size_t)bb * P + p) * HW + hh] = v[i];
-                                        if (++hh == HW) { hh = 0; ++bb; }
-                                    }
-                                }
-                            }
-                            hw += 4;
-                            while (hw >= HW) { hw -= HW; ++b; }
-                        }
-                    }
+                if (skip_epi) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(TEMPTY(acc));
+                    acc ^= 1;
+                    if (acc == 0) acc_par ^= 1u;
+                    continue;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(TEMPTY(acc));
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + h * hcols);
+                uint32_t r0[32], r1[32];
+                const bool do_ld = !(prm.debug & 2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
+                if (do_ld) tmem_ld32(taddr, r0);
+                tmem_ld_wait();
+#pragma unroll 1
+                for (int c = 0; c < nch; c += 2) {
+                    if (do_ld) tmem_ld32(taddr + (uint32_t)(c + 1) * 32u, r1);
+                    epilogue_chunk<LAYOUT>(r0, sn_g + c * 32, c0, c1, c2, nbase + c * 32, p, pok, prm);
+                    tmem_ld_wait();
+                    if (c + 2 < nch) {
+                        if (do_ld) tmem_ld32(taddr + (uint32_t)(c + 2) * 32u, r0);
+                    } else {                                      // accumulator fully in registers: release it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(TEMPTY(acc));
+                    }
+                    epilogue_chunk<LAYOUT>(r1, sn_g + (c + 1) * 32, c0, c1, c2, nbase + (c + 1) * 32, p, pok, prm);
+                    if (c + 2 < nch) tmem_ld_wait();
+                }
                 acc ^= 1;
                 if (acc == 0) acc_par ^= 1u;
             }
@@ -408,7 +520,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -460,7 +572,7 @@ WsLayout ws_layout(long long N, int P, int D) {
     w.flag = o; o = align256(o + 4);
     w.ah = o; o = align256(o + (size_t)N * 2 * D * 2);
     w.al = o; o = align256(o + (size_t)N * 2 * D * 2);
-    w.sn = o; o = align256(o + (size_t)N * 4);
+    w.sn = o; o = align256(o + (size_t)((N + 255) / 256 * 256) * 4);
     w.total = o;
     return w;
 }
@@ -506,30 +618,38 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     TcParams prm;
     prm.e0 = e0; prm.e1 = e1; prm.e2 = e2; prm.sn = sn; prm.noniso = flag; prm.out = out;
     prm.N = (int)N; prm.HW = HW; prm.P = P; prm.D = D;
-    prm.n_ntiles = (int)((N + NT - 1) / NT);
+    {
+        const char* dbg = getenv("MGP_TC_DEBUG");
+        prm.debug = dbg ? atoi(dbg) : 0;
+    }
     prm.n_ptiles = (P + PT - 1) / PT;
     int dev = 0, sms = 148;
     MGP_CUDA(cudaGetDevice(&dev));
     MGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // split the prototype tiles of an n-tile into groups so that there are >= ~8 units per CTA
-    int ppu = prm.n_ptiles;
-    while (ppu > 1 && (long long)prm.n_ntiles * ((prm.n_ptiles + ppu - 1) / ppu) < 8LL * sms) ppu = (ppu + 1) / 2;
-    prm.ppu = ppu;
-    prm.n_pgroups = (prm.n_ptiles + ppu - 1) / ppu;
-    prm.n_units = prm.n_ntiles * prm.n_pgroups;
-    const int x_blocks = 2 * (2 * D / KB);
-    const size_t fixed = (size_t)x_blocks * SUB_BYTES + 1024 /*align*/ + 1024 /*barriers + sn*/;
+    int min_units = 0x7fffffff;
+    for (int v = 0; v < 2; ++v) {
+        const int nt = v ? 256 : 128;
+        prm.n_ntiles[v] = (int)((N + nt - 1) / nt);
+        // split the prototype tiles of an n-tile into groups so that there are >= ~8 units per CTA
+        int ppu = prm.n_ptiles;
+        while (ppu > 1 && (long long)prm.n_ntiles[v] * ((prm.n_ptiles + ppu - 1) / ppu) < 8LL * sms) ppu = (ppu + 1) / 2;
+        prm.ppu[v] = ppu;
+        prm.n_pgroups[v] = (prm.n_ptiles + ppu - 1) / ppu;
+        prm.n_units[v] = prm.n_ntiles[v] * prm.n_pgroups[v];
+        if (prm.n_units[v] < min_units) min_units = prm.n_units[v];
+    }
+    const size_t fixed = (size_t)1024 * D /*x tile*/ + 1024 /*align*/ + 2048 /*barriers + sn tile*/;
     int stages = (int)((227 * 1024 - fixed) / (2 * SUB_BYTES));
     if (stages > 6) stages = 6;
     if (stages < 2) return MGP_ERR_UNSUPPORTED;
     prm.stages = stages;
     const size_t smem = fixed + (size_t)stages * 2 * SUB_BYTES;
-    const int grid = prm.n_units < sms ? prm.n_units : sms;
+    const int grid = min_units < sms ? min_units : sms;
 
 #define MGP_TC_LAUNCH(L)                                                                                           \
     do {                                                                                                           \
         MGP_CUDA(cudaFuncSetAttribute(logprob_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        logprob_tc_kernel<L><<<grid, 256, smem, st>>>(mxh, mxl, mph, mpl, prm);                                     \
+        logprob_tc_kernel<L><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mph, mpl, prm);                                     \
     } while (0)
     if (layout == MGP_OUT_LOGP_NP) MGP_TC_LAUNCH(MGP_OUT_LOGP_NP);
     else if (layout == MGP_OUT_LOGP_BPHW) MGP_TC_LAUNCH(MGP_OUT_LOGP_BPHW);

@@ -241,38 +241,6 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
         v[4 * j4 + 2] = fmaf(c1, __uint_as_float(r[4 * j4 + 2]), fmaf(c2, s.z, c0));
         v[4 * j4 + 3] = fmaf(c1, __uint_as_float(r[4 * j4 + 3]), fmaf(c2, s.w, c0));
     }
-    if (LAYOUT == MGP_OUT_LOGP_NP && (P & 3) == 0) {
-        // Transpose 4x4 blocks inside each lane quad (4 shuffles per block) so that a thread owns 4
-        // CONSECUTIVE prototypes of one patch row: 8 x STG.128 per thread instead of 32 x STG.32, and a
-        // warp instruction covers 4 rows x 128 B.  (Measured on B200: 8 warps/SM of coalesced STG.32
-        // sustain 3.0 TB/s, the same pattern as STG.128 5.5 TB/s -- tools/micro/store_bw.cu.)
-        const int lane = threadIdx.x & 31;
-        const int l = lane & 3;
-        const bool t1 = (l & 1) != 0, t2 = (l & 2) != 0;
-        const int pq = p - l;                                 // first prototype of the quad
-        const bool qok = pq + 3 < P;                          // P % 4 == 0: a quad is valid or not as a whole
-        float* row = prm.out + (size_t)(n0 + l) * P + pq;
-        const size_t step = (size_t)4 * P;
-        const bool dbg_nostore = (prm.debug & 1) != 0;
-        float sink = 0.f;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const float a0 = v[4 * m], a1 = v[4 * m + 1], a2 = v[4 * m + 2], a3 = v[4 * m + 3];
-            const float r0 = __shfl_xor_sync(0xffffffffu, t1 ? a0 : a1, 1);
-            const float r1 = __shfl_xor_sync(0xffffffffu, t1 ? a2 : a3, 1);
-            // column (0+t1) and column (2+t1), each as (even row, odd row) of the lane pair
-            const float c01e = t1 ? r0 : a0, c01o = t1 ? a1 : r0;
-            const float c23e = t1 ? r1 : a2, c23o = t1 ? a3 : r1;
-            const float ze = __shfl_xor_sync(0xffffffffu, t2 ? c01e : c23e, 2);
-            const float zo = __shfl_xor_sync(0xffffffffu, t2 ? c01o : c23o, 2);
-            const float ke = t2 ? c23e : c01e, ko = t2 ? c23o : c01o;
-            const float4 b = t2 ? make_float4(ze, zo, ke, ko) : make_float4(ke, ko, ze, zo);
-            if (dbg_nostore) { sink += b.x + b.y + b.z + b.w; continue; }
-            if (qok && n0 + 4 * m + l < N) *reinterpret_cast<float4*>(row + (size_t)m * step) = b;
-        }
-        if (dbg_nostore && sink == 123.456f) prm.out[0] = sink;
-        return;
-    }
     if (!pok) return;
     if (prm.debug & 1) {
         float acc = 0.f;
@@ -490,26 +458,25 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                     continue;
                 }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + h * hcols);
-                uint32_t r0[32], r1[32];
                 const bool do_ld = !(prm.debug & 2);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
-                if (do_ld) tmem_ld32(taddr, r0);
-                tmem_ld_wait();
 #pragma unroll 1
                 for (int c = 0; c < nch; c += 2) {
-                    if (do_ld) tmem_ld32(taddr + (uint32_t)(c + 1) * 32u, r1);
-                    epilogue_chunk<LAYOUT>(r0, sn_g + c * 32, c0, c1, c2, nbase + c * 32, p, pok, prm);
+                    uint32_t r0[32], r1[32];
+                    if (do_ld) {
+                        tmem_ld32(taddr + (uint32_t)c * 32u, r0);
+                        tmem_ld32(taddr + (uint32_t)(c + 1) * 32u, r1);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
+                    }
                     tmem_ld_wait();
-                    if (c + 2 < nch) {
-                        if (do_ld) tmem_ld32(taddr + (uint32_t)(c + 2) * 32u, r0);
-                    } else {                                      // accumulator fully in registers: release it
+                    if (c + 2 >= nch) {                           // accumulator fully in registers: release it
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(TEMPTY(acc));
                     }
+                    epilogue_chunk<LAYOUT>(r0, sn_g + c * 32, c0, c1, c2, nbase + c * 32, p, pok, prm);
                     epilogue_chunk<LAYOUT>(r1, sn_g + (c + 1) * 32, c0, c1, c2, nbase + (c + 1) * 32, p, pok, prm);
-                    if (c + 2 < nch) tmem_ld_wait();
                 }
                 acc ^= 1;
                 if (acc == 0) acc_par ^= 1u;

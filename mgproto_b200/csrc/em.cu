@@ -49,30 +49,47 @@ em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_le
 // ---------------------------------------------------------------------------------------------
 // E-step for one row held by a warp: lane l owns elements d = 4*(l + 32 j) .. +3, j < VEC4.
 // Returns the log-normaliser; lane k (and k+32) keeps the smoothed responsibility of component k.
-template <int VEC4>
-__device__ __forceinline__ float warp_estep_row(const float4 (&xv)[VEC4], const float* __restrict__ s_mu,
+template <int VEC4, int KBLK>
+__device__ __forceinline__ float warp_estep_rowb(const float4 (&xv)[VEC4], const float* __restrict__ s_mu,
                                                 const float* __restrict__ s_rinv, const float* __restrict__ s_cst,
                                                 int K, int D, int lane, float alpha, float& r_lo, float& r_hi,
                                                 float& lr_lo, float& lr_hi) {
     float w_lo = -INFINITY, w_hi = -INFINITY;
-    for (int k = 0; k < K; ++k) {
-        float q = 0.f;
+    for (int k0 = 0; k0 < K; k0 += KBLK) {
+        float q[KBLK];
 #pragma unroll
-        for (int j = 0; j < VEC4; ++j) {
-            const int d = 4 * (lane + 32 * j);
-            if (d >= D) continue;
-            const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + d);
-            const float4 r = *reinterpret_cast<const float4*>(s_rinv + k * D + d);
-            float t;
-            t = (xv[j].x - m.x) * r.x; q = fmaf(t, t, q);
-            t = (xv[j].y - m.y) * r.y; q = fmaf(t, t, q);
-            t = (xv[j].z - m.z) * r.z; q = fmaf(t, t, q);
-            t = (xv[j].w - m.w) * r.w; q = fmaf(t, t, q);
+        for (int i = 0; i < KBLK; ++i) {
+            q[i] = 0.f;
+            const int k = k0 + i;
+            if (k < K) {
+#pragma unroll
+                for (int j = 0; j < VEC4; ++j) {
+                    const int d = 4 * (lane + 32 * j);
+                    if (d >= D) continue;
+                    const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + d);
+                    const float4 r = *reinterpret_cast<const float4*>(s_rinv + k * D + d);
+                    float t;
+                    t = (xv[j].x - m.x) * r.x; q[i] = fmaf(t, t, q[i]);
+                    t = (xv[j].y - m.y) * r.y; q[i] = fmaf(t, t, q[i]);
+                    t = (xv[j].z - m.z) * r.z; q[i] = fmaf(t, t, q[i]);
+                    t = (xv[j].w - m.w) * r.w; q[i] = fmaf(t, t, q[i]);
+                }
+            }
         }
-        q = warp_sum(q);
-        const float wl = s_cst[k] - 0.5f * q;       // lp + log(pi + eps)   (ref :316)
-        if (lane == (k & 31)) {
-            if (k < 32) w_lo = wl; else w_hi = wl;
+        // KBLK independent butterflies: the shuffles of different components overlap
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < KBLK; ++i) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+#pragma unroll
+        for (int i = 0; i < KBLK; ++i) {
+            const int k = k0 + i;
+            if (k < K) {
+                const float wl = s_cst[k] - 0.5f * q[i];   // lp + log(pi + eps)   (ref :316)
+                if (lane == (k & 31)) {
+                    if (k < 32) w_lo = wl; else w_hi = wl;
+                }
+            }
         }
     }
     const float mx = warp_max(fmaxf(w_lo, w_hi));
@@ -82,14 +99,21 @@ __device__ __forceinline__ float warp_estep_row(const float4 (&xv)[VEC4], const 
     const float norm = mx + logf(se);               // logsumexp (ref :318)
     lr_lo = w_lo - norm;                            // log_resp (ref :319)
     lr_hi = w_hi - norm;
-    const float den = 1.0f + (float)K * alpha;      // sum_k (resp + alpha) with sum resp = se/se
-    // the reference normalises by the actual sum of (resp + alpha); resp sums to 1 up to rounding
-    const float rs = warp_sum(((lane < K) ? expf(lr_lo) : 0.f) + ((lane + 32 < K) ? expf(lr_hi) : 0.f));
-    const float den2 = rs + (float)K * alpha;
-    (void)den;
-    r_lo = (lane < K) ? (expf(lr_lo) + alpha) / den2 : 0.f;        // ref :380-383
-    r_hi = (lane + 32 < K) ? (expf(lr_hi) + alpha) / den2 : 0.f;
+    // smoothed responsibility (ref :380-383): (resp + alpha) / sum_k(resp + alpha); resp sums to one
+    // (up to an ulp), so the denominator is 1 + K alpha
+    const float inv_se = 1.0f / se, inv_den = 1.0f / (1.0f + (float)K * alpha);
+    r_lo = (lane < K) ? fmaf(e_lo, inv_se, alpha) * inv_den : 0.f;
+    r_hi = (lane + 32 < K) ? fmaf(e_hi, inv_se, alpha) * inv_den : 0.f;
     return norm;
+}
+
+template <int VEC4>
+__device__ __forceinline__ float warp_estep_row(const float4 (&xv)[VEC4], const float* __restrict__ s_mu,
+                                                const float* __restrict__ s_rinv, const float* __restrict__ s_cst,
+                                                int K, int D, int lane, float alpha, float& r_lo, float& r_hi,
+                                                float& lr_lo, float& lr_hi) {
+    if (K % 5 == 0) return warp_estep_rowb<VEC4, 5>(xv, s_mu, s_rinv, s_cst, K, D, lane, alpha, r_lo, r_hi, lr_lo, lr_hi);
+    return warp_estep_rowb<VEC4, 8>(xv, s_mu, s_rinv, s_cst, K, D, lane, alpha, r_lo, r_hi, lr_lo, lr_hi);
 }
 
 constexpr int RB = 32;  // rows per batch
@@ -134,10 +158,17 @@ em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
     __syncthreads();
 
     float a1[NOUT], a2[NOUT];
-#pragma unroll
-    for (int i = 0; i < NOUT; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
-    float a0 = 0.f, ll = 0.f;
+    int ok_[NOUT], od_[NOUT];                 // component / dim of each owned output (-1: none)
     const int KD = K * D;
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) {
+        a1[i] = 0.f;
+        a2[i] = 0.f;
+        const int o = tid + 256 * i;
+        ok_[i] = (o < KD) ? o / D : -1;
+        od_[i] = (o < KD) ? o - (o / D) * D : 0;
+    }
+    float a0 = 0.f, ll = 0.f;
 
     for (int r0 = seg_b; r0 < seg_e; r0 += RB) {
         const int nr = min(RB, seg_e - r0);
@@ -164,11 +195,9 @@ em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
         for (int rl = 0; rl < nr; ++rl) {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) {
-                const int o = tid + 256 * i;
-                if (o < KD) {
-                    const int k = o / D, d = o - k * D;
-                    const float xx = s_x[rl * D + d];
-                    const float rx = s_r[rl * K + k] * xx;
+                if (ok_[i] >= 0) {
+                    const float xx = s_x[rl * D + od_[i]];
+                    const float rx = s_r[rl * K + ok_[i]] * xx;
                     a1[i] += rx;
                     if (WITH_S2) a2[i] = fmaf(rx, xx, a2[i]);
                 }
@@ -243,17 +272,54 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
             count = num_em_loop * (n_active - ord - 1);
         }
         if (count <= 0) return;
-        for (int o = tid; o < KD; o += 256) {
-            float p = mu_c[o], m = exp_avg[(size_t)c * KD + o], v = exp_avg_sq[(size_t)c * KD + o];
-            double b1p = pow((double)adam.beta1, (double)first), b2p = pow((double)adam.beta2, (double)first);
-            for (int s = 0; s < count; ++s) {
-                b1p *= (double)adam.beta1;
-                b2p *= (double)adam.beta2;
-                adam_apply(p, m, v, 0.f, adam, b1p, b2p);
+        // With g = 0 Adam's moments just decay: m_s = b1^s m_0, v_s = b2^s v_0, and
+        //   p <- p - [lr b1^s / (1 - b1^(first+s))] * m_0 / (sqrt(v_0) * b2^(s/2) / sqrt(1 - b2^(first+s)) + eps).
+        // The bracketed scalars c_s, d_s are the same for every element: tabulate them in shared memory
+        // (double precision pow once per step), then each element costs one FMA + one reciprocal per step.
+        extern __shared__ float sm[];
+        constexpr int TAB = 2048;
+        float* s_c = sm;            // [TAB]
+        float* s_d = sm + TAB;      // [TAB]
+        float p_[8], a_[8], m0_[8];
+        for (int ob = 0; ob < KD; ob += 256 * 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int o = ob + tid + 256 * i;
+                if (o < KD) {
+                    p_[i] = mu_c[o];
+                    m0_[i] = exp_avg[(size_t)c * KD + o];
+                    a_[i] = sqrtf(exp_avg_sq[(size_t)c * KD + o]);
+                }
             }
-            mu_c[o] = p;
-            exp_avg[(size_t)c * KD + o] = m;
-            exp_avg_sq[(size_t)c * KD + o] = v;
+            for (int s0 = 0; s0 < count; s0 += TAB) {
+                const int ns = min(TAB, count - s0);
+                __syncthreads();
+                for (int s = tid; s < ns; s += 256) {
+                    const double st = (double)(s0 + s + 1);
+                    const double b1s = pow((double)adam.beta1, st), b2s = pow((double)adam.beta2, st);
+                    const double b1t = pow((double)adam.beta1, (double)first + st);
+                    const double b2t = pow((double)adam.beta2, (double)first + st);
+                    s_c[s] = (float)((double)adam.lr * b1s / (1.0 - b1t));
+                    s_d[s] = (float)(sqrt(b2s) / sqrt(1.0 - b2t));
+                }
+                __syncthreads();
+                for (int s = 0; s < ns; ++s) {
+                    const float cs = s_c[s], ds = s_d[s];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) p_[i] = fmaf(-cs * m0_[i], __frcp_rn(fmaf(a_[i], ds, adam.eps)), p_[i]);
+                }
+            }
+            const float mdec = (float)pow((double)adam.beta1, (double)count);
+            const float vdec = (float)pow((double)adam.beta2, (double)count);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int o = ob + tid + 256 * i;
+                if (o < KD) {
+                    mu_c[o] = p_[i];
+                    exp_avg[(size_t)c * KD + o] = m0_[i] * mdec;
+                    exp_avg_sq[(size_t)c * KD + o] *= vdec;
+                }
+            }
         }
         return;
     }
@@ -261,8 +327,8 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
     // phase 1: one EM-loop step of an active class
     if (ord < 0) return;
     if (only_class >= 0 && c != only_class) return;
-    extern __shared__ float sm[];
-    float* s_mu = sm;               // [K][D]
+    extern __shared__ float sm1[];
+    float* s_mu = sm1;              // [K][D]
     float* s_e = s_mu + KD;         // [K][K] exp(-|mu_i - mu_j|^2)
     float* s_s0 = s_e + K * K;      // [K]
     const int lane = tid & 31, warp = tid >> 5;
@@ -464,7 +530,8 @@ extern "C" int mgp_em_update(const float* stats, int n_split, int with_s2, int n
     if (phase == 1 && (!stats || n_split <= 0 || n_rows_total <= 0)) return MGP_ERR_INVALID;
     if ((exp_avg == nullptr) != (exp_avg_sq == nullptr)) return MGP_ERR_INVALID;
     const size_t stride = mgp_em_stat_stride(K, D, with_s2);
-    const size_t smem = ((size_t)K * D + (size_t)K * K + K) * sizeof(float);
+    size_t smem = ((size_t)K * D + (size_t)K * K + K) * sizeof(float);
+    if (smem < 2 * 2048 * sizeof(float)) smem = 2 * 2048 * sizeof(float);
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
     MGP_CUDA(cudaFuncSetAttribute(em_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AdamCfg a{lr, beta1, beta2, adam_eps};

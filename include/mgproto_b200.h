@@ -37,6 +37,9 @@ extern "C" {
 #define MGP_MATH_FP32 0     /* exact-form fp32 SIMT: sum_d ((x-mu)/(sigma+eps))^2          */
 #define MGP_MATH_TC 1       /* tcgen05 tensor cores, fp16 hi/lo split x3, fp32 accumulate  */
 #define MGP_MATH_AUTO 2     /* TC when the shape qualifies, else FP32                      */
+#define MGP_MATH_TC_REUSE 3 /* TC, operands (fp16 hi/lo split of x and of the prototypes) are
+                               already staged in `ws` by the previous MGP_MATH_TC call with the
+                               same shapes and pointers: only the GEMM kernel is launched       */
 
 /* output layouts of mgp_logprob_fwd */
 #define MGP_OUT_LOGP_NP 0      /* out[n*P + p]           = log p      (ref: compute_log_prob)   */

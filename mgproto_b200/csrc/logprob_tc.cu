@@ -556,7 +556,8 @@ bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D) {
 size_t mgp_logprob_tc_ws_bytes(long long N, int P, int D) { return ws_layout(N, P, D).total; }
 
 int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log, float* out,
-                          int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+                          int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes, int reuse_operands,
+                          cudaStream_t st) {
     const long long N = (long long)B * HW;
     const WsLayout w = ws_layout(N, P, D);
     if (ws_bytes < w.total) return MGP_ERR_WORKSPACE;
@@ -571,11 +572,13 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     float* sn = reinterpret_cast<float*>(wsb + w.sn);
     int* flag = reinterpret_cast<int*>(wsb + w.flag);
 
-    MGP_CUDA(cudaMemsetAsync(flag, 0, 4, st));
-    tc_proto_prep_kernel<<<(P + 7) / 8, 256, 0, st>>>(mu, sigma, eps, eps_log, bh, bl, e0, e1, e2, flag, P, D);
-    MGP_CHECK_LAUNCH();
-    tc_x_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(xhat, ah, al, sn, flag, (int)N, D);
-    MGP_CHECK_LAUNCH();
+    if (!reuse_operands) {
+        MGP_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+        tc_proto_prep_kernel<<<(P + 7) / 8, 256, 0, st>>>(mu, sigma, eps, eps_log, bh, bl, e0, e1, e2, flag, P, D);
+        MGP_CHECK_LAUNCH();
+        tc_x_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(xhat, ah, al, sn, flag, (int)N, D);
+        MGP_CHECK_LAUNCH();
+    }
 
     CUtensorMap mxh, mxl, mph, mpl;
     if (!make_map(&mxh, ah, (uint64_t)N, 2 * D) || !make_map(&mxl, al, (uint64_t)N, 2 * D) ||

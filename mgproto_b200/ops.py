@@ -9,14 +9,14 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_OUT_LOGP_BPHW, MGP_OUT_LOGP_NP,
-                   MGP_OUT_NEGP_BPHW, check)
+from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_REUSE, MGP_OUT_LOGP_BPHW,
+                   MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, check)
 
 __all__ = ["normalize_fwd", "logprob", "head_select", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
            "bank_linearize", "em_plan", "em_stats", "em_update", "em_estep", "em_mstep_closed", "push_argmin",
            "MATH_MODES"]
 
-MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO}
+MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE}
 
 _launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -70,7 +70,7 @@ def normalize_fwd(x_bdhw: torch.Tensor, want_nchw: bool = False):
 
 # ----------------------------------------------------------------------------------- a2/a3/a16
 def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, eps=0.0, eps_log=0.0,
-            math="auto"):
+            math="auto", ws=None, out=None, return_ws=False):
     """ref model.py:256-275 / :323-336.  xhat [N,D], mu/sigma [P,D] ->
     layout NP: [N,P] log p;  BPHW: [B,P,HW] log p;  NEGP: [B,P,HW] -exp(log p)."""
     x = _req(xhat_nd, torch.float32, "xhat")
@@ -82,20 +82,27 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
         raise RuntimeError("mgproto_b200: mu/sigma must be [P, D]")
     if layout == MGP_OUT_LOGP_NP:
         B_, HW_ = N, 1
-        out = torch.empty((N, P), device=x.device, dtype=torch.float32)
+        shape = (N, P)
     else:
         if B is None or HW is None or B * HW != N:
             raise RuntimeError("mgproto_b200: BPHW layouts need B*HW == N")
         B_, HW_ = B, HW
-        out = torch.empty((B, P, HW), device=x.device, dtype=torch.float32)
+        shape = (B, P, HW)
+    if out is None:
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    elif tuple(out.shape) != shape:
+        raise RuntimeError("mgproto_b200: out has the wrong shape")
     lib = _lib.load()
     m = _math(math)
     nbytes = lib.mgp_logprob_ws_bytes(B_, HW_, P, D, m)
-    ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
+    if ws is None:
+        ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
+    elif ws.numel() < nbytes:
+        raise RuntimeError("mgproto_b200: workspace too small")
     check(lib.mgp_logprob_fwd(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), float(eps), float(eps_log), out.data_ptr(),
                               int(layout), B_, HW_, P, D, m, ws.data_ptr(), nbytes, _stream()), "mgp_logprob_fwd")
-    _count(4 if nbytes > (P * D + P) * 4 else 2)
-    return out
+    _count(1 if m == MGP_MATH_TC_REUSE else (3 if nbytes > (P * D + P) * 4 else 2))
+    return (out, ws) if return_ws else out
 
 
 # ----------------------------------------------------------------------------------- a4-a7

@@ -195,13 +195,10 @@ def build_model(dev, seed=0):
 
 
 def loss_fn(out, gt):
-    """CE on level 0 + 0.2 * mean CE over the mining levels (ref train_and_test.py:37-41, :55), written as one
-    log-softmax over the class axis instead of T separate cross_entropy calls (same value and gradient)."""
-    import torch
-    B, C, T = out.shape
-    nll = -torch.log_softmax(out, dim=1).gather(1, gt.view(B, 1, 1).expand(B, 1, T)).squeeze(1)   # [B, T]
-    ce = nll.mean(0)
-    return ce[0] + 0.2 * ce[1:].mean()
+    """CE on level 0 + 0.2 * mean CE over the mining levels (ref train_and_test.py:37-41, :55) -- the library's
+    fused value+gradient helper (one launch instead of the ~25 ATen launches of T separate cross_entropy calls)."""
+    from mgproto_b200 import ops
+    return ops.mine_cross_entropy(out, gt, 0.2)
 
 
 def main():

@@ -179,6 +179,13 @@ int mgp_em_estep(const float* x, const float* mu, const float* sigma, const floa
 int mgp_em_mstep_closed(const float* x, const float* log_resp, float alpha, float* pi_out,
                         float* mu_out, float* sigma_out, int n, int K, int D, void* stream);
 
+/* ---- a17  training loss on the head output (optional fused helper) ------------------------------
+ * ref: train_and_test.py:37-41, :55.  out [B,C,T] log evidences, gt [B] ->
+ *   loss_b [B] per-image shares of  CE(level 0) + mine_coef * mean_{t>=1} CE(level t)  (sum = the loss),
+ *   grad [B,C,T] = d loss / d out.  gt must lie in [0, C). */
+int mgp_mine_ce(const float* out, const int64_t* gt, float* loss_b, float* grad, int B, int C, int T,
+                float mine_coef, void* stream);
+
 /* ---- f1  prototype projection search --------------------------------------------------------
  * ref: push.py:125-158.  For every image and the K prototypes of its label's class: flat HW
  * argmin of -p (= argmax of log p; ties: smaller index) and -p there.

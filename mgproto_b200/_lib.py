@@ -38,6 +38,7 @@ SIGNATURES = {
                            _f, _f, _f, _f, _f, _f, _vp, _i, _i, _i, _i, _vp]),
     "mgp_em_estep": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_mstep_closed": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mgp_mine_ce": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mgp_push_argmin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 

@@ -20,7 +20,6 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
     int* ucount = sm;       // [B] unique rows of image b
     int* cls = sm + B;      // [B] class or -1
     int* wr_m = sm + 2 * B; // [B] rows accepted for the class if b is the class's first image, else -1
-    constexpr int T = 1;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const long long c = gt[b];
         if (c < 0 || c >= C) {
@@ -30,20 +29,23 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
             continue;
         }
         cls[b] = (int)c;
-        const int32_t* top1 = top1_bk + (size_t)b * K;
+        const int32_t* top1g = top1_bk + (size_t)b * K;
+        int top1[64];                                         // K <= 64 (checked on the host)
+        for (int k = 0; k < K; ++k) top1[k] = top1g[k];
         int u = 0;
         for (int k = 0; k < K; ++k) {
-            const int v = top1[(size_t)k * T];
+            const int v = top1[k];
             bool first = true;
-            for (int k2 = 0; k2 < k; ++k2) first = first && (top1[(size_t)k2 * T] != v);
+            for (int k2 = 0; k2 < k; ++k2) first = first && (top1[k2] != v);
             int rank = -1;
             if (first) {
-                rank = 0;  // number of distinct smaller values = ascending position (torch.unique order)
+                // ascending position among the distinct values (torch.unique order): count distinct smaller ones
+                rank = 0;
                 for (int k2 = 0; k2 < K; ++k2) {
-                    const int v2 = top1[(size_t)k2 * T];
+                    const int v2 = top1[k2];
                     if (v2 < v) {
                         bool f2 = true;
-                        for (int k3 = 0; k3 < k2; ++k3) f2 = f2 && (top1[(size_t)k3 * T] != v2);
+                        for (int k3 = 0; k3 < k2; ++k3) f2 = f2 && (top1[k3] != v2);
                         rank += f2 ? 1 : 0;
                     }
                 }
@@ -163,7 +165,7 @@ extern "C" int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, ui
                                 int cap, void* stream) {
     if (!bank || !mem_len || !head || !updated || !rows || !top1 || !gt || !plan) return MGP_ERR_INVALID;
     if (B <= 0 || C <= 0 || K <= 0 || D <= 0 || cap <= 0 || (D & 3)) return MGP_ERR_INVALID;
-    if (B > 8192) return MGP_ERR_UNSUPPORTED;
+    if (B > 8192 || K > 64) return MGP_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     size_t smem = (size_t)3 * B * sizeof(int);
     MGP_CUDA(cudaFuncSetAttribute(enqueue_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -174,32 +174,46 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
 // shared-memory list; warp w owns rows n with (n & 7) == w and walks the list, so the
 // accumulation is atomics-free and deterministic.
 __global__ void proto_weight_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
-                                    float* __restrict__ w, float* __restrict__ wm, size_t n) {
+                                    float* __restrict__ w, float* __restrict__ wm, float* __restrict__ wsc,
+                                    int* __restrict__ noniso, size_t n, int D) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        float s = sigma[i];
-        float ww = 1.0f / (s * s);
+        const float s = sigma[i];
+        const float ww = 1.0f / (s * s);
         w[i] = ww;
         wm[i] = ww * mu[i];
+        const size_t p = i / D;
+        if (i == p * D) wsc[p] = ww;
+        if (s != sigma[p * D]) atomicOr(noniso, 1);          // sigma varies over d inside a prototype
     }
 }
 
-constexpr int BCAP = 640;   // entries per owner-warp bucket
+constexpr int LCAP = 2304;   // entries per drain (>= P + K(T-1) of the labelled cfg: one drain per image)
 
+// grid (B, D/DC), DC = 64.  Warp w owns the 8-dim column slice [8w, 8w+8) of every row of the image's
+// gradient tile G[HW][DC]: all warps walk the whole (compacted, fixed-order) entry list, four entries per
+// step (lane = 8*j + dim), so the work is balanced however the mined patches cluster, there are no
+// atomics and the summation order is fixed.  The prototype / patch row loads of the four entries are
+// issued together; the read-modify-write of G is serialised over j because entries often share a row.
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, const float* __restrict__ vals,
                 const int32_t* __restrict__ idx, const float* __restrict__ weight, const int64_t* __restrict__ gt,
                 const float* __restrict__ xhat, const float* __restrict__ w, const float* __restrict__ wm,
-                float* __restrict__ g_xhat, int HW, int C, int K, int D, int T, int DC) {
+                const float* __restrict__ wsc, const int* __restrict__ noniso, float* __restrict__ g_xhat, int HW,
+                int C, int K, int D, int T, int DC) {
     extern __shared__ float smem[];
-    const int pitch = DC + 2;                               // even: float2 accesses stay 8 B aligned
+    const int pitch = DC + 1;
+    const bool aniso = (*noniso != 0);
     float* G = smem;                                        // [HW][pitch]
-    unsigned* lkey = reinterpret_cast<unsigned*>(G + (size_t)HW * pitch);     // [8][BCAP] p*1024 + n
-    float* lval = reinterpret_cast<float*>(lkey + 8 * BCAP);                  // [8][BCAP]
-    float* Qs = lval + 8 * BCAP;                            // [C]  sum_t gl/exp(logit)      (wrong-class fold)
+    unsigned* lkey = reinterpret_cast<unsigned*>(G + (size_t)HW * pitch);     // [LCAP] p*1024 + n
+    float* lval = reinterpret_cast<float*>(lkey + LCAP);    // [LCAP]
+    unsigned* skey = reinterpret_cast<unsigned*>(lval + LCAP);                // [LCAP] sorted by row
+    float* sval = reinterpret_cast<float*>(skey + LCAP);    // [LCAP]
+    int* bins = reinterpret_cast<int*>(sval + LCAP);        // [HW + 1] row histogram / start offsets
+    float* Qs = reinterpret_cast<float*>(bins + HW + 1);    // [C]  sum_t gl/exp(logit)      (wrong-class fold)
     float* qg = Qs + C;                                     // [T]  gl/exp(logit) of the GT class
-    __shared__ int wcount[8][8];                            // [producer warp][owner bucket]
-    __shared__ int bcount[8];
+    __shared__ int wcount[8];
+    __shared__ int lcount;
 
     const int b = blockIdx.x;
     const int d0 = blockIdx.y * DC;
@@ -223,13 +237,15 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                 qg[t] = gl[lo + t] / expf(logits[lo + t]);
             }
     }
-    if (threadIdx.x < 8) bcount[threadIdx.x] = 0;
+    if (threadIdx.x == 0) lcount = 0;
     __syncthreads();
 
     // entry space: with labels only level 0 of every prototype plus levels 1..T-1 of the GT class carry
     // gradient (wrong-class levels alias level 0, ref model.py:221); without labels all P*T entries
     const bool gvalid = has_gt && g >= 0 && g < C;
     const int E = has_gt ? (P + (gvalid ? K * (T - 1) : 0)) : P * T;
+    const int jj = lane >> 3, dd = warp * 8 + (lane & 7);   // entry slot / owned dim of this lane
+    const bool dok = dd < dc;
     for (int e0 = 0; e0 < E; e0 += 256) {
         const int e = e0 + threadIdx.x;
         float a = 0.f;
@@ -259,72 +275,126 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
             a = qv * __ldg(weight + (size_t)c * P + p) * vals[vi];
             key = (unsigned)p * 1024u + (unsigned)idx[vi];
         }
-        // ordered compaction into the bucket of the warp that owns row n ((n & 7) == owner)
         const bool keep = (a != 0.f);
-        const int owner = key & 7u;
-        unsigned mybal = 0;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const unsigned bal = __ballot_sync(0xffffffffu, keep && owner == o);
-            if (lane == 0) wcount[warp][o] = __popc(bal);
-            if (owner == o) mybal = bal;
-        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wcount[warp] = __popc(bal);
         __syncthreads();
+        int base = lcount;
+        for (int wv = 0; wv < warp; ++wv) base += wcount[wv];
         if (keep) {
-            int pos = bcount[owner];
-            for (int wv = 0; wv < warp; ++wv) pos += wcount[wv][owner];
-            pos += __popc(mybal & ((1u << lane) - 1u));
-            lkey[owner * BCAP + pos] = key;
-            lval[owner * BCAP + pos] = a;
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            lkey[pos] = key;
+            lval[pos] = a;
         }
         __syncthreads();
-        if (threadIdx.x < 8) {
+        if (threadIdx.x == 0) {
             int tot = 0;
-            for (int wv = 0; wv < 8; ++wv) tot += wcount[wv][threadIdx.x];
-            bcount[threadIdx.x] += tot;
+            for (int wv = 0; wv < 8; ++wv) tot += wcount[wv];
+            lcount += tot;
         }
         __syncthreads();
-        int mx = 0;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) mx = max(mx, bcount[o]);
+        const int cnt = lcount;
         const bool last = (e0 + 256 >= E);
-        if (mx + 256 > BCAP || last) {
-            // drain: warp `warp` accumulates its own rows -- no atomics, fixed order.  Four entries are
-            // fetched together so that their (L2-latency) prototype / patch row loads overlap.
-            const int cnt = bcount[warp];
-            const unsigned* mk = lkey + warp * BCAP;
-            const float* mv = lval + warp * BCAP;
-            for (int i0 = 0; i0 < cnt; i0 += 4) {
-                float2 fw[4], fm[4], fx[4];
-                float aa[4];
-                int nn[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = min(i0 + j, cnt - 1);
-                    const unsigned kk = mk[i];
-                    aa[j] = (i0 + j < cnt) ? mv[i] : 0.f;
-                    const int p = kk >> 10;
-                    nn[j] = kk & 1023u;
-                    fw[j] = fm[j] = fx[j] = make_float2(0.f, 0.f);
-                    if (2 * lane < dc) {
-                        fw[j] = __ldg(reinterpret_cast<const float2*>(w + (size_t)p * D + d0) + lane);
-                        fm[j] = __ldg(reinterpret_cast<const float2*>(wm + (size_t)p * D + d0) + lane);
-                        fx[j] = __ldg(reinterpret_cast<const float2*>(xhat + ((size_t)b * HW + nn[j]) * D + d0) + lane);
-                    }
+        if (cnt + 256 > LCAP || last) {
+            // Each lane (slot jj, dim dd) walks entries jj, jj+4, ...; 16 entries (4 per lane) are fetched per
+            // step so their L2 loads overlap.  Contributions to the lane's current row are summed in a
+            // register and written to G only when the row changes (mined patches cluster on few rows);
+            // the write-back is serialised over the 4 slots because slots may hold the same row.
+            // Stable counting sort of the entries by patch row (one warp, MATCH.ANY ranks: deterministic).
+            // Mined patches cluster on a few dozen rows, so after the sort a lane meets long runs of one row.
+            for (int i = threadIdx.x; i <= HW; i += 256) bins[i] = 0;
+            __syncthreads();
+            if (warp == 0) {
+                for (int i0 = 0; i0 < cnt; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int n = (i < cnt) ? (int)(lkey[i] & 1023u) : (0x10000 + lane);
+                    const unsigned m = __match_any_sync(0xffffffffu, n);
+                    if (i < cnt && (m & ((1u << lane) - 1u)) == 0) bins[n + 1] += __popc(m);
+                    __syncwarp();
                 }
+                // exclusive prefix over rows (HW <= 1024)
+                int carry = 0;
+                for (int r0 = 0; r0 <= HW; r0 += 32) {
+                    const int r = r0 + lane;
+                    int v = (r <= HW) ? bins[r] : 0;
+                    int x = v;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float2* gr = reinterpret_cast<float2*>(G + (size_t)nn[j] * pitch) + lane;
-                    if (2 * lane < dc) {
-                        float2 acc = *gr;
-                        acc.x += aa[j] * (fm[j].x - fw[j].x * fx[j].x);
-                        acc.y += aa[j] * (fm[j].y - fw[j].y * fx[j].y);
-                        *gr = acc;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int y = __shfl_up_sync(0xffffffffu, x, o);
+                        if (lane >= o) x += y;
                     }
+                    if (r <= HW) bins[r] = carry + x;          // inclusive sum of counts up to row r-1 (bins[0] = 0)
+                    carry += __shfl_sync(0xffffffffu, x, 31);
+                    __syncwarp();
+                }
+                for (int i0 = 0; i0 < cnt; i0 += 32) {
+                    const int i = i0 + lane;
+                    const unsigned kk = (i < cnt) ? lkey[i] : 0u;
+                    const int n = (i < cnt) ? (int)(kk & 1023u) : (0x10000 + lane);
+                    const unsigned m = __match_any_sync(0xffffffffu, n);
+                    if (i < cnt) {
+                        const int pos = bins[n] + __popc(m & ((1u << lane) - 1u));
+                        skey[pos] = kk;
+                        sval[pos] = lval[i];
+                    }
+                    __syncwarp();
+                    if (i < cnt && (m & ((1u << lane) - 1u)) == 0) bins[n] += __popc(m);
+                    __syncwarp();
                 }
             }
             __syncthreads();
-            if (threadIdx.x < 8) bcount[threadIdx.x] = 0;
+            // G[n] += sum_e a_e * wm_p  -  xhat_n * sum_e a_e * w_p : both sums are kept in registers for the
+            // lane's current row; xhat is touched only at write-back, and w_p is a per-prototype scalar when
+            // every sigma is isotropic (one row load per entry instead of three)
+            int cur_n = -1;
+            float s1 = 0.f, s2 = 0.f;
+            const float* xcol = xhat + (size_t)b * HW * D + d0 + dd;
+            for (int i0 = 0; i0 < cnt; i0 += 16) {
+                float fw[4], fm[4], aa[4];
+                int nn[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int i = i0 + 4 * h + jj;
+                    const bool ok = i < cnt;
+                    const unsigned kk = ok ? skey[i] : 0u;
+                    aa[h] = ok ? sval[i] : 0.f;
+                    const int p = kk >> 10;
+                    nn[h] = ok ? (int)(kk & 1023u) : -1;
+                    fw[h] = fm[h] = 0.f;
+                    if (ok && dok) {
+                        fm[h] = __ldg(wm + (size_t)p * D + d0 + dd);
+                        fw[h] = aniso ? __ldg(w + (size_t)p * D + d0 + dd) : __ldg(wsc + p);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const bool valid = nn[h] >= 0;
+                    const bool flush = valid && cur_n >= 0 && nn[h] != cur_n;
+                    if (__any_sync(0xffffffffu, flush)) {
+                        const float xv = (flush && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (jj == j && flush && dok) G[(size_t)cur_n * pitch + dd] += s1 - xv * s2;
+                            __syncwarp();
+                        }
+                    }
+                    if (valid) {
+                        if (nn[h] != cur_n) { cur_n = nn[h]; s1 = 0.f; s2 = 0.f; }
+                        s1 = fmaf(aa[h], fm[h], s1);
+                        s2 = fmaf(aa[h], fw[h], s2);
+                    }
+                }
+            }
+            {
+                const float xv = (cur_n >= 0 && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (jj == j && cur_n >= 0 && dok) G[(size_t)cur_n * pitch + dd] += s1 - xv * s2;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) lcount = 0;
             __syncthreads();
         }
     }
@@ -333,6 +403,43 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
         float* dst = g_xhat + ((size_t)b * HW + n) * D + d0;
         const float* gr = G + (size_t)n * pitch;
         for (int d = lane; d < dc; d += 32) dst[d] = gr[d];
+    }
+}
+
+// a17 helper: the training loss on the head's output (ref train_and_test.py:37-41, :55)
+//   loss = CE(out[:,:,0], gt) + mine_coef * mean_{t>=1} CE(out[:,:,t], gt),   CE = mean over the batch
+// One CTA per image computes, for every level t, logsumexp_c out[b,c,t]; writes the image's loss share and
+// d loss / d out[b,:,:] (softmax - onehot, weighted) in the same pass -- one launch instead of ~25 ATen ones.
+__global__ void __launch_bounds__(256)
+mine_ce_kernel(const float* __restrict__ out, const int64_t* __restrict__ gt, float* __restrict__ loss_b,
+               float* __restrict__ grad, int B, int C, int T, float mine_coef) {
+    extern __shared__ float sm[];
+    float* lse = sm;            // [T]
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* ob = out + (size_t)b * C * T;
+    for (int t = warp; t < T; t += 8) {
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, ob[(size_t)c * T + t]);
+        m = warp_max(m);
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += expf(ob[(size_t)c * T + t] - m);
+        se = warp_sum(se);
+        if (lane == 0) lse[t] = m + logf(se);
+    }
+    __syncthreads();
+    const long long g = gt[b];
+    const float wt0 = 1.0f / (float)B, wtm = (T > 1) ? mine_coef / ((float)(T - 1) * (float)B) : 0.f;
+    if (threadIdx.x == 0) {
+        float l = 0.f;
+        for (int t = 0; t < T; ++t) l += (t == 0 ? wt0 : wtm) * (lse[t] - ob[(size_t)g * T + t]);
+        loss_b[b] = l;
+    }
+    float* gb = grad + (size_t)b * C * T;
+    for (int i = threadIdx.x; i < C * T; i += 256) {
+        const int c = i / T, t = i - c * T;
+        const float wv = (t == 0) ? wt0 : wtm;
+        gb[i] = wv * (expf(ob[i] - lse[t]) - (((long long)c == g) ? 1.0f : 0.0f));
     }
 }
 
@@ -397,7 +504,7 @@ extern "C" int mgp_head_select(const float* logp_bphw, const float* weight_cp, c
 }
 
 extern "C" size_t mgp_head_bwd_ws_bytes(int B, int HW, int P, int D) {
-    return ((size_t)2 * P * D + (size_t)B * HW * D) * sizeof(float);
+    return ((size_t)2 * P * D + (size_t)B * HW * D + (size_t)P + 64) * sizeof(float);
 }
 
 extern "C" int mgp_head_bwd(const float* grad_logits, const float* logits, const float* vals, const int32_t* idx,
@@ -415,21 +522,29 @@ extern "C" int mgp_head_bwd(const float* grad_logits, const float* logits, const
     float* w = reinterpret_cast<float*>(ws);
     float* wm = w + (size_t)P * D;
     float* g_xhat = wm + (size_t)P * D;
+    float* wsc = g_xhat + (size_t)B * HW * D;
+    int* noniso = reinterpret_cast<int*>(wsc + P);
     const size_t npd = (size_t)P * D;
-    proto_weight_kernel<<<(unsigned)((npd + 255) / 256), 256, 0, st>>>(mu, sigma, w, wm, npd);
+    MGP_CUDA(cudaMemsetAsync(noniso, 0, sizeof(int), st));
+    proto_weight_kernel<<<(unsigned)((npd + 255) / 256), 256, 0, st>>>(mu, sigma, w, wm, wsc, noniso, npd, D);
     MGP_CHECK_LAUNCH();
-    int DC = 64;                                             // D-chunk per CTA (one float2 per lane): 2 CTAs per SM
-    while (DC > 32 && (size_t)HW * (DC + 2) * 4 > 64 * 1024) DC >>= 1;
-    if (DC > D) DC = ((D + 31) / 32) * 32;
-    if (DC > 64 || (D & 1)) return MGP_ERR_UNSUPPORTED;
-    size_t smem = (size_t)HW * (DC + 2) * 4 + (size_t)8 * BCAP * 8 + (size_t)(C + T) * 4;
+    const int DC = 64;                                       // D-chunk per CTA: 8 warps x 8 dims
+    size_t smem = (size_t)HW * (DC + 1) * 4 + (size_t)LCAP * 16 + (size_t)(HW + 1 + C + T) * 4;
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
     MGP_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(B, (D + DC - 1) / DC);
-    head_bwd_kernel<<<grid, 256, smem, st>>>(grad_logits, logits, vals, idx, weight_cp, gt, xhat_nd, w, wm, g_xhat, HW,
-                                             C, K, D, T, DC);
+    head_bwd_kernel<<<grid, 256, smem, st>>>(grad_logits, logits, vals, idx, weight_cp, gt, xhat_nd, w, wm, wsc, noniso,
+                                             g_xhat, HW, C, K, D, T, DC);
     MGP_CHECK_LAUNCH();
     return mgp_normalize_bwd(g_xhat, xhat_nd, inv_norm, g_x_nchw, B, D, HW, stream);
+}
+
+extern "C" int mgp_mine_ce(const float* out, const int64_t* gt, float* loss_b, float* grad, int B, int C, int T,
+                           float mine_coef, void* stream) {
+    if (!out || !gt || !loss_b || !grad || B <= 0 || C <= 0 || T <= 0) return MGP_ERR_INVALID;
+    mine_ce_kernel<<<B, 256, (size_t)T * sizeof(float), (cudaStream_t)stream>>>(out, gt, loss_b, grad, B, C, T, mine_coef);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
 }
 
 extern "C" int mgp_push_argmin(const float* logp_bphw, const int64_t* labels, int32_t* arg, float* val, int B, int HW,

@@ -13,7 +13,7 @@ from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_REUSE,
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, check)
 
 __all__ = ["normalize_fwd", "logprob", "head_select", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
-           "bank_linearize", "em_plan", "em_stats", "em_update", "em_estep", "em_mstep_closed", "push_argmin",
+           "bank_linearize", "em_plan", "em_stats", "em_update", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
 MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE}
@@ -286,6 +286,34 @@ def em_mstep_closed(x_nd, log_resp_nk, alpha):
                                           sg.data_ptr(), n, K, D, _stream()), "mgp_em_mstep_closed")
     _count(1)
     return pi, mu, sg
+
+
+# ----------------------------------------------------------------------------------- a17 (optional)
+class MineCEFunction(torch.autograd.Function):
+    """loss = CE(out[:,:,0], gt) + mine_coef * mean_{t>=1} CE(out[:,:,t], gt) (ref train_and_test.py:37-41,:55)
+    with value and gradient from one kernel."""
+
+    @staticmethod
+    def forward(ctx, out, gt, mine_coef):
+        o = _req(out.contiguous(), torch.float32, "output")
+        g = _req(gt.contiguous(), torch.int64, "target")
+        B, C, T = o.shape
+        loss_b = torch.empty((B,), device=o.device, dtype=torch.float32)
+        grad = torch.empty_like(o)
+        check(_lib.load().mgp_mine_ce(o.data_ptr(), g.data_ptr(), loss_b.data_ptr(), grad.data_ptr(), B, C, T,
+                                      float(mine_coef), _stream()), "mgp_mine_ce")
+        _count(1)
+        ctx.save_for_backward(grad)
+        return loss_b.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def mine_cross_entropy(out, gt, mine_coef=0.2):
+    return MineCEFunction.apply(out, gt, float(mine_coef))
 
 
 # ----------------------------------------------------------------------------------- f1

@@ -356,3 +356,76 @@ def test_logprob_tc_baseline_size_properties():
     lp_b = ops.logprob(x, mu, sg, 1, B=B, HW=HW, math="tc")
     assert torch.equal(lp_b, lp.view(B, HW, P).permute(0, 2, 1).contiguous())
     assert torch.isfinite(lp).all()
+
+
+def test_mine_cross_entropy_matches_torch():
+    """Fused loss helper == CE(level 0) + 0.2 * mean CE(levels 1..T-1) of train_and_test.py:37-41,:55."""
+    from mgproto_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, C, T = 37, 23, 7
+    out = (torch.randn(B, C, T, generator=g) * 3 - 5).to(_dev()).requires_grad_(True)
+    gt = torch.randint(0, C, (B,), generator=g).to(_dev())
+    ref = _loss(out, gt)
+    gref, = torch.autograd.grad(ref, out)
+    out2 = out.detach().clone().requires_grad_(True)
+    got = ops.mine_cross_entropy(out2, gt, 0.2)
+    (got * 1.7).backward()
+    torch.testing.assert_close(got, ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out2.grad, 1.7 * gref, rtol=1e-4, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] shapes (prototype sweep K x D) and configs[4] (OoD scoring) as parity cases
+@pytest.mark.parametrize("K,D", [(5, 64), (20, 128), (40, 64), (10, 256), (5, 512)])
+def test_head_sweep_shapes_vs_fp64(K, D):
+    """forward logits / top-T values for the sweep shapes against a float64 torch restatement of
+    model.py:208-254 (tensor-core path where the shape qualifies, exact SIMT path otherwise)."""
+    from mgproto_b200 import ops
+    C, B, H, W, T = 8, 3, 14, 14, 20
+    g = torch.Generator().manual_seed(K * 1000 + D)
+    x = torch.randn(B, D, H, W, generator=g).to(_dev())
+    mu = F.normalize(torch.rand(C, K, D, generator=g), dim=2).to(_dev())
+    sg = torch.full((C, K, D), 1 / np.sqrt(2 * np.pi), device=_dev())
+    pi = torch.softmax(torch.randn(C, K, generator=g), dim=1)
+    wt = torch.zeros(C, C * K)
+    for c in range(C):
+        wt[c, c * K:(c + 1) * K] = pi[c]
+    wt = wt.to(_dev())
+    gt = torch.randint(0, C, (B,), generator=g).to(_dev())
+    lg, _, idx = ops.head_forward(x, mu, sg, wt, gt, T, "auto")
+    xd = F.normalize(x.double(), dim=1).permute(0, 2, 3, 1).reshape(B, H * W, D)
+    lp = (-0.5 * D * np.log(2 * np.pi) - sg.double().log().sum(-1).view(1, 1, -1)
+          - 0.5 * (((xd[:, :, None, :] - mu.double().view(1, 1, C * K, D)) / sg.double().view(1, 1, C * K, D)) ** 2).sum(-1))
+    v, _ = torch.topk(lp.exp().permute(0, 2, 1), T, dim=2)                     # [B,P,T]
+    wrong = (torch.arange(C * K, device=_dev()) // K)[None, :] != gt[:, None]
+    v = torch.where(wrong[:, :, None], v[:, :, :1].expand(-1, -1, T), v)
+    ref = torch.log(torch.einsum("bpt,cp->bct", v, wt.double()))
+    torch.testing.assert_close(lg.double(), ref, rtol=RTOL, atol=1e-6)
+
+
+def test_ood_score_auroc_matches_oracle():
+    """configs[4]: OoD score sum_c exp(logit_c0) (ref train_and_test.py:184-199) on synthetic in-dist / OoD
+    features: scores within 1e-4 and AUROC equal to the oracle's."""
+    from sklearn.metrics import roc_auc_score
+    from mgproto_b200 import ops
+    from oracle import mgproto_oracle as O
+    C, K, D, H, W, n = 6, 4, 64, 7, 7, 24
+    g = torch.Generator().manual_seed(9)
+    mu = F.normalize(torch.rand(C, K, D, generator=g), dim=2)
+    sg = torch.full((C, K, D), 1 / np.sqrt(2 * np.pi))
+    wt = torch.zeros(C, C * K)
+    for c in range(C):
+        wt[c, c * K:(c + 1) * K] = 1.0 / K
+    pick = torch.randint(0, C * K, (n, H * W), generator=g)
+    x_in = (mu.view(C * K, D)[pick] + 0.1 * torch.randn(n, H * W, D, generator=g)).permute(0, 2, 1).reshape(n, D, H, W)
+    x_out = torch.randn(n, D, H, W, generator=g)
+    x = torch.cat([x_in, x_out]).contiguous()
+    lg, _, _ = ops.head_forward(x.to(_dev()), mu.to(_dev()), sg.to(_dev()), wt.to(_dev()), None, 1, "auto")
+    score = lg[:, :, 0].exp().sum(1).cpu().numpy()
+    fw = O.head_forward(x.numpy().astype(np.float64), mu.numpy().astype(np.float64), sg.numpy().astype(np.float64),
+                        wt.numpy().astype(np.float64), None, 1)
+    ref = np.exp(fw["logits"][:, :, 0]).sum(1)
+    np.testing.assert_allclose(score, ref, rtol=RTOL)
+    y = np.r_[np.ones(n), np.zeros(n)]
+    assert abs(roc_auc_score(y, score) - roc_auc_score(y, ref)) < 1e-9
+    assert roc_auc_score(y, ref) > 0.9

@@ -31,7 +31,10 @@
 
 namespace {
 
-constexpr int NT_MAX = 256;      // patches per tile (UMMA N): 256 when sigma is isotropic, else 128
+constexpr int NT_MAX = 256;      // patches per tile (UMMA N): 256 (192 with the TMA-store epilogue) when sigma is
+                                 // isotropic, else 128
+constexpr int LAYOUT_NP_TMA = 3; // internal: [N,P] output written by TMA bulk tensor stores from a shared-memory stage
+constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // one [32 patches x 32 prototypes] fp32 block per epilogue warp
 constexpr int PT = 128;          // prototypes per tile (UMMA M)
 constexpr int KB = 64;           // K elements per smem block (128 B rows, SWIZZLE_128B)
 constexpr int SUB_BYTES = 128 * KB * 2;   // one [128 x 64] fp16 block = 16 KiB
@@ -85,6 +88,11 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 // 8-row groups of 1024 B, 16-byte chunks XOR-ed with the row index
 __host__ __device__ __forceinline__ uint32_t swz_off(int r, int k) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -219,17 +227,20 @@ struct TcParams {
     const int* noniso;
     float* out;
     int N, HW, P, D;
-    int n_ptiles, stages;
-    int debug;   // ablation switches for profiling (MGP_TC_DEBUG): 1 no global stores, 2 no TMEM loads, 4 no MMAs
-    // schedule for [0] the general (NT=128) and [1] the isotropic (NT=256) variant; picked on the device by the flag
-    int n_ntiles[2], ppu[2], n_pgroups[2], n_units[2];
+    int n_ntiles, n_ptiles;
+    int team;              // CTAs per team: the CTAs of a team work on the SAME x tile at the same time, on
+                           // adjacent prototype tiles, so each output row receives team*512 contiguous bytes at once
+    uint32_t smem_bytes;   // dynamic shared memory of the launch
+    int debug;   // ablation switches for profiling (MGP_TC_DEBUG): 1 no global stores, 2 no TMEM loads, 4 no MMAs,
+                 // 8 no epilogue work, 16 no prototype TMA loads
 };
 
 constexpr int TC_THREADS = 384;   // warps: 0 proto TMA, 1 MMA, 2 TMEM alloc, 3 x-tile TMA, 4..11 epilogue
 
 template <int LAYOUT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const float* __restrict__ s_sn_c, float c0,
-                                               float c1, float c2, int n0, int p, bool pok, const TcParams& prm) {
+                                               float c1, float c2, int n0, int p, bool pok, const TcParams& prm,
+                                               float* stg = nullptr, const CUtensorMap* map_out = nullptr) {
     const int N = prm.N, P = prm.P, HW = prm.HW;
     float v[32];
     const float4* s4 = reinterpret_cast<const float4*>(s_sn_c);    // |x_n|^2 of the 32 columns (shared memory)
@@ -240,6 +251,23 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
         v[4 * j4 + 1] = fmaf(c1, __uint_as_float(r[4 * j4 + 1]), fmaf(c2, s.y, c0));
         v[4 * j4 + 2] = fmaf(c1, __uint_as_float(r[4 * j4 + 2]), fmaf(c2, s.z, c0));
         v[4 * j4 + 3] = fmaf(c1, __uint_as_float(r[4 * j4 + 3]), fmaf(c2, s.w, c0));
+    }
+    if (LAYOUT == LAYOUT_NP_TMA) {
+        // stage the [32 patches x 32 prototypes] block in shared memory (row = patch, 128 B) and hand it to
+        // the TMA engine: the global writes are issued asynchronously as whole row segments, the warp only
+        // pays 32 conflict-free STS.  Out-of-range rows / columns are clipped by the tensor map.
+        const int lane = threadIdx.x & 31;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous block has been read
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[j * 32 + lane] = v[j];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && !(prm.debug & 1)) {
+            tma_store_2d(map_out, smem_u32(stg), p - lane, n0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
     }
     if (!pok) return;
     if (prm.debug & 1) {
@@ -286,48 +314,57 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                   const __grid_constant__ CUtensorMap map_ph, const __grid_constant__ CUtensorMap map_pl,
-                  const TcParams prm) {
+                  const __grid_constant__ CUtensorMap map_out, const TcParams prm) {
+    constexpr bool TMA_ST = (LAYOUT == LAYOUT_NP_TMA);
+    constexpr int NT = 128;                                       // patches per tile = UMMA N
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
 
     const bool gen = (*prm.noniso != 0);
-    const int var = gen ? 0 : 1;
-    const int NT = gen ? 128 : 256;                               // same x-tile bytes either way: NT * Kg * 4
     const int nkb = (gen ? 2 * prm.D : prm.D) / KB;               // K blocks per tile
     const int kcol0 = gen ? 0 : prm.D;                            // isotropic: only the [x] / [-2 w mu] half
-    const int S = prm.stages;
-    const int n_pgroups = prm.n_pgroups[var], ppu = prm.ppu[var], n_units = prm.n_units[var];
-    const uint32_t xsub = (uint32_t)NT * KB * 2;                  // one [NT x 64] fp16 block of the x tile
     const uint32_t idesc = make_idesc(NT);
+    const int n_ptiles = prm.n_ptiles, n_ntiles = prm.n_ntiles;
 
-    // carve-up: x tile (1024*D bytes) | S stages of (proto hi, proto lo) | barriers
+    // carve-up: nbuf x tiles | S stages of (proto hi, proto lo) | [TMA-store staging] | barriers + sn tile
+    const uint32_t x_bytes = (uint32_t)(2 * nkb) * SUB_BYTES;     // hi blocks then lo blocks
+    const uint32_t tile_budget = prm.smem_bytes - 1024u - 2048u - (TMA_ST ? (uint32_t)STAGING_BYTES : 0u);
+    const int nbuf = (2 * x_bytes + 2 * 2 * SUB_BYTES <= tile_budget) ? 2 : 1;   // double-buffer x when it fits
+    int S = (int)((tile_budget - nbuf * x_bytes) / (2 * SUB_BYTES));
+    if (S > 6) S = 6;
     const uint32_t x_base = base;
-    const uint32_t st_base = x_base + 1024u * (uint32_t)prm.D;
-    const uint32_t misc = st_base + (uint32_t)S * 2 * SUB_BYTES;
+    const uint32_t st_base = x_base + nbuf * x_bytes;
+    const uint32_t stg_base = st_base + (uint32_t)S * 2 * SUB_BYTES;
+    const uint32_t misc = stg_base + (TMA_ST ? (uint32_t)STAGING_BYTES : 0u);
+    float* staging = reinterpret_cast<float*>(base_ptr + (stg_base - base));
     uint8_t* misc_ptr = base_ptr + (misc - base);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(misc_ptr);       // full[S] empty[S] xfull xempty tfull[2] tempty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc_ptr);       // full[6] empty[6] xfull[2] xempty[2] tfull[2] tempty[2]
     const uint32_t bar0 = misc;
-    auto FULL = [&](int s) { return bar0 + 8u * s; };
-    auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
-    const uint32_t XFULL = bar0 + 8u * (2 * S), XEMPTY = bar0 + 8u * (2 * S + 1);
-    auto TFULL = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * S + 4 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
-    float* s_sn = reinterpret_cast<float*>(bars + 2 * S + 8);     // [NT_MAX] |x|^2 of the current n-tile
+    auto FULL = [&](int i) { return bar0 + 8u * i; };
+    auto EMPTY = [&](int i) { return bar0 + 8u * (6 + i); };
+    auto XFULL = [&](int i) { return bar0 + 8u * (12 + i); };
+    auto XEMPTY = [&](int i) { return bar0 + 8u * (14 + i); };
+    auto TFULL = [&](int i) { return bar0 + 8u * (16 + i); };
+    auto TEMPTY = [&](int i) { return bar0 + 8u * (18 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    float* s_sn = reinterpret_cast<float*>(bars + 22);            // [2][NT] |x|^2 of the x tiles, 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        mbar_init(XFULL, 1);
-        mbar_init(XEMPTY, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 8); }
+        for (int i = 0; i < 6; ++i) { mbar_init(FULL(i), 1); mbar_init(EMPTY(i), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(XFULL(i), 1);
+            mbar_init(XEMPTY(i), 1);
+            mbar_init(TFULL(i), 1);
+            mbar_init(TEMPTY(i), 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -335,58 +372,56 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // contiguous range of work units for this CTA; unit = (n-tile, group of `ppu` prototype tiles)
-    const int u_begin = (int)(((long long)n_units * blockIdx.x) / gridDim.x);
-    const int u_end = (int)(((long long)n_units * (blockIdx.x + 1)) / gridDim.x);
+    // schedule: team t = blockIdx / team handles x tiles t, t + n_teams, ...; member k of the team takes the
+    // prototype tiles k, k + team, ... of each of them
+    const int TS = prm.team;
+    const int n_teams = gridDim.x / TS, team = blockIdx.x / TS, k0 = blockIdx.x % TS;
+    const bool has_work = (team < n_teams) && (k0 < n_ptiles);
 
-    if (warp == 3 && lane == 0) {
-        // =========================== x-tile TMA producer ===========================
-        if (u_begin < u_end) {
-            const int nt_first = u_begin / n_pgroups, nt_last = (u_end - 1) / n_pgroups;
-            for (int nt = nt_first, c = 0; nt <= nt_last; ++nt, ++c) {
-                if (c >= 1) mbar_wait(XEMPTY, (uint32_t)((c - 1) & 1));
-                mbar_expect_tx(XFULL, (uint32_t)(2 * nkb) * xsub);
-                for (int kb = 0; kb < nkb; ++kb)
-                    for (int r = 0; r < NT; r += 128) {           // TMA box = 128 rows
-                        const uint32_t ro = (uint32_t)r * KB * 2;
-                        tma_load_2d(x_base + (uint32_t)kb * xsub + ro, &map_xh, kcol0 + kb * KB, nt * NT + r, XFULL);
-                        tma_load_2d(x_base + (uint32_t)(nkb + kb) * xsub + ro, &map_xl, kcol0 + kb * KB, nt * NT + r, XFULL);
-                    }
+    if (!has_work) {
+        // nothing to do for this CTA (tiny problems)
+    } else if (warp == 3 && lane == 0) {
+        // =========================== x-tile TMA producer (next x tile prefetched when double-buffered) ===========
+        int c = 0;
+        for (int nt = team; nt < n_ntiles; nt += n_teams, ++c) {
+            const int buf = c % nbuf;
+            if (c >= nbuf) mbar_wait(XEMPTY(buf), (uint32_t)((c / nbuf - 1) & 1));
+            mbar_expect_tx(XFULL(buf), x_bytes);
+            const uint32_t xb = x_base + (uint32_t)buf * x_bytes;
+            for (int kb = 0; kb < nkb; ++kb) {
+                tma_load_2d(xb + (uint32_t)kb * SUB_BYTES, &map_xh, kcol0 + kb * KB, nt * NT, XFULL(buf));
+                tma_load_2d(xb + (uint32_t)(nkb + kb) * SUB_BYTES, &map_xl, kcol0 + kb * KB, nt * NT, XFULL(buf));
             }
         }
     } else if (warp == 0 && lane == 0) {
         // =========================== prototype TMA producer ===========================
         int stage = 0;
         uint32_t phase = 0;
-        for (int u = u_begin; u < u_end; ++u) {
-            const int pg = u % n_pgroups;
-            const int pt_end = min(prm.n_ptiles, (pg + 1) * ppu);
-            for (int pt = pg * ppu; pt < pt_end; ++pt) {
+        for (int nt = team; nt < n_ntiles; nt += n_teams) {
+            for (int pt = k0; pt < n_ptiles; pt += TS) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(EMPTY(stage), phase ^ 1u);
-                    if (prm.debug & 16) { mbar_arrive(FULL(stage)); if (++stage == S) { stage = 0; phase ^= 1u; } continue; }
-                    mbar_expect_tx(FULL(stage), 2 * SUB_BYTES);
-                    const uint32_t dst = st_base + (uint32_t)stage * 2 * SUB_BYTES;
-                    tma_load_2d(dst, &map_ph, kcol0 + kb * KB, pt * PT, FULL(stage));
-                    tma_load_2d(dst + SUB_BYTES, &map_pl, kcol0 + kb * KB, pt * PT, FULL(stage));
+                    if (prm.debug & 16) {
+                        mbar_arrive(FULL(stage));
+                    } else {
+                        mbar_expect_tx(FULL(stage), 2 * SUB_BYTES);
+                        const uint32_t dst = st_base + (uint32_t)stage * 2 * SUB_BYTES;
+                        tma_load_2d(dst, &map_ph, kcol0 + kb * KB, pt * PT, FULL(stage));
+                        tma_load_2d(dst + SUB_BYTES, &map_pl, kcol0 + kb * KB, pt * PT, FULL(stage));
+                    }
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // =========================== MMA issuer ===========================
-        int stage = 0, acc = 0;
+        int stage = 0, acc = 0, c = 0;
         uint32_t phase = 0, acc_par = 0;
-        int cur_nt = -1, c = -1;
-        for (int u = u_begin; u < u_end; ++u) {
-            const int nt = u / n_pgroups, pg = u - nt * n_pgroups;
-            if (nt != cur_nt) {
-                ++c;
-                mbar_wait(XFULL, (uint32_t)(c & 1));
-                cur_nt = nt;
-            }
-            const int pt_end = min(prm.n_ptiles, (pg + 1) * ppu);
-            for (int pt = pg * ppu; pt < pt_end; ++pt) {
+        for (int nt = team; nt < n_ntiles; nt += n_teams, ++c) {
+            const int buf = c % nbuf;
+            mbar_wait(XFULL(buf), (uint32_t)((c / nbuf) & 1));
+            const uint32_t xb = x_base + (uint32_t)buf * x_bytes;
+            for (int pt = k0; pt < n_ptiles; pt += TS) {
                 mbar_wait(TEMPTY(acc), acc_par ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NT);
@@ -394,13 +429,13 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                     mbar_wait(FULL(stage), phase);
                     tc_fence_after();
                     const uint32_t ph = st_base + (uint32_t)stage * 2 * SUB_BYTES, pl = ph + SUB_BYTES;
-                    const uint32_t xh = x_base + (uint32_t)kb * xsub, xl = x_base + (uint32_t)(nkb + kb) * xsub;
+                    const uint32_t xh = xb + (uint32_t)kb * SUB_BYTES, xl = xb + (uint32_t)(nkb + kb) * SUB_BYTES;
 #pragma unroll
                     for (int k = 0; k < KB / 16; ++k) {
+                        if (prm.debug & 4) continue;
                         const uint32_t off = (uint32_t)k * 32u;   // 16 fp16 = 32 B inside the 128 B swizzle row
                         const uint64_t a_h = umma_desc(ph + off), a_l = umma_desc(pl + off);
                         const uint64_t b_h = umma_desc(xh + off), b_l = umma_desc(xl + off);
-                        if (prm.debug & 4) continue;
                         tc_mma_f16(d_tmem, a_h, b_h, idesc, (kb | k) != 0);
                         tc_mma_f16(d_tmem, a_l, b_h, idesc, 1u);
                         tc_mma_f16(d_tmem, a_h, b_l, idesc, 1u);
@@ -412,36 +447,30 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                 acc ^= 1;
                 if (acc == 0) acc_par ^= 1u;
             }
-            const int next_nt = (u + 1 < u_end) ? (u + 1) / n_pgroups : -1;
-            if (next_nt != cur_nt) tc_commit(XEMPTY);             // x tile may be refilled
+            tc_commit(XEMPTY(buf));                               // x buffer may be refilled
         }
     } else if (warp >= 4) {
         // =========================== epilogue ===========================
-        // 8 warps drain each accumulator together: warp = (TMEM lane quarter q, column half h).  Inside a
-        // warp the tcgen05.ld of the next 32 columns is in flight while the current 32 are stored.
+        // 8 warps drain each accumulator together: warp = (TMEM lane quarter q, column half h)
         const int e = warp - 4;
         const int q = e & 3, h = e >> 2;
         const int et = q * 32 + lane;                             // prototype row within the tile (TMEM lane)
-        const int hcols = NT / 2, nch = hcols / 32;               // 2 (NT=128) or 4 (NT=256) chunks per warp
-        int acc = 0;
+        constexpr int hcols = NT / 2;                             // 64 columns = 2 chunks per warp
+        float* stg = staging + e * 1024;                          // this warp's 4 KiB TMA-store block
+        int acc = 0, c = 0;
         uint32_t acc_par = 0;
-        int cur_nt = -1;
         const bool skip_epi = (prm.debug & 8) != 0;
-        for (int u = u_begin; u < u_end; ++u) {
-            const int nt = u / n_pgroups, pg = u - nt * n_pgroups;
-            const int pt_end = min(prm.n_ptiles, (pg + 1) * ppu);
-            const int nbase = nt * NT + h * hcols;
-            const float* sn_g = s_sn + h * hcols;
-            if (nt != cur_nt) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int i = e * 32 + lane; i < NT; i += 256) {
-                    const int n = nt * NT + i;
-                    s_sn[i] = (n < prm.N) ? prm.sn[n] : 0.f;
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                cur_nt = nt;
+        for (int nt = team; nt < n_ntiles; nt += n_teams, ++c) {
+            float* sn_t = s_sn + (c & 1) * NT;                    // double-buffered: no barrier against readers of c-1
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // ... but c-2's readers must be done
+            for (int i = e * 32 + lane; i < NT; i += 256) {
+                const int n = nt * NT + i;
+                sn_t[i] = (n < prm.N) ? prm.sn[n] : 0.f;
             }
-            for (int pt = pg * ppu; pt < pt_end; ++pt) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int nbase = nt * NT + h * hcols;
+            const float* sn_g = sn_t + h * hcols;
+            for (int pt = k0; pt < n_ptiles; pt += TS) {
                 const int p = pt * PT + et;
                 const bool pok = p < prm.P;
                 const float c0 = pok ? __ldg(prm.e0 + p) : 0.f;
@@ -449,45 +478,38 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                 const float c2 = (pok && !gen) ? __ldg(prm.e2 + p) : 0.f;
                 mbar_wait(TFULL(acc), acc_par);
                 tc_fence_after();
-                if (skip_epi) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(TEMPTY(acc));
-                    acc ^= 1;
-                    if (acc == 0) acc_par ^= 1u;
-                    continue;
-                }
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + h * hcols);
-                const bool do_ld = !(prm.debug & 2);
-#pragma unroll 1
-                for (int c = 0; c < nch; c += 2) {
+                if (!skip_epi) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + h * hcols);
                     uint32_t r0[32], r1[32];
-                    if (do_ld) {
-                        tmem_ld32(taddr + (uint32_t)c * 32u, r0);
-                        tmem_ld32(taddr + (uint32_t)(c + 1) * 32u, r1);
+                    if (!(prm.debug & 2)) {
+                        tmem_ld32(taddr, r0);
+                        tmem_ld32(taddr + 32u, r1);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
                     }
                     tmem_ld_wait();
-                    if (c + 2 >= nch) {                           // accumulator fully in registers: release it
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(TEMPTY(acc));
-                    }
-                    epilogue_chunk<LAYOUT>(r0, sn_g + c * 32, c0, c1, c2, nbase + c * 32, p, pok, prm);
-                    epilogue_chunk<LAYOUT>(r1, sn_g + (c + 1) * 32, c0, c1, c2, nbase + (c + 1) * 32, p, pok, prm);
+                    tc_fence_before();                            // accumulator is in registers: release it
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(TEMPTY(acc));
+                    epilogue_chunk<LAYOUT>(r0, sn_g, c0, c1, c2, nbase, p, pok, prm, stg, &map_out);
+                    epilogue_chunk<LAYOUT>(r1, sn_g + 32, c0, c1, c2, nbase + 32, p, pok, prm, stg, &map_out);
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(TEMPTY(acc));
                 }
                 acc ^= 1;
                 if (acc == 0) acc_par ^= 1u;
             }
         }
+        if (TMA_ST && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
     }
 }
 
@@ -511,15 +533,28 @@ EncodeTiledFn get_encode() {
 }
 
 // [rows, cols] fp16 row-major, box = 64 cols x 128 rows, 128 B swizzle; OOB rows read as zero
-bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols) {
+bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * sizeof(__half)};
-    cuuint32_t box[2] = {KB, 128};
+    cuuint32_t box[2] = {KB, box_rows};
     cuuint32_t es[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// output [N, P] fp32 row-major, box = 32 prototypes x 32 patches, no swizzle (TMA-store epilogue)
+bool make_out_map(CUtensorMap* m, const void* ptr, uint64_t N, uint64_t P) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {P, N};
+    cuuint64_t strides[1] = {P * sizeof(float)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -581,8 +616,13 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     }
 
     CUtensorMap mxh, mxl, mph, mpl;
-    if (!make_map(&mxh, ah, (uint64_t)N, 2 * D) || !make_map(&mxl, al, (uint64_t)N, 2 * D) ||
-        !make_map(&mph, bh, (uint64_t)P, 2 * D) || !make_map(&mpl, bl, (uint64_t)P, 2 * D))
+    CUtensorMap mout;
+    const char* no_tma = getenv("MGP_TC_NO_TMA_STORE");
+    const bool tma_store = (layout == MGP_OUT_LOGP_NP) && (P % 4 == 0) && !(no_tma && atoi(no_tma));
+    if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, 128) || !make_map(&mxl, al, (uint64_t)N, 2 * D, 128) ||
+        !make_map(&mph, bh, (uint64_t)P, 2 * D, 128) || !make_map(&mpl, bl, (uint64_t)P, 2 * D, 128))
+        return MGP_ERR_UNSUPPORTED;
+    if (!make_out_map(&mout, tma_store ? out : (float*)ah, tma_store ? (uint64_t)N : 64, tma_store ? (uint64_t)P : 64))
         return MGP_ERR_UNSUPPORTED;
 
     TcParams prm;
@@ -593,35 +633,36 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
         prm.debug = dbg ? atoi(dbg) : 0;
     }
     prm.n_ptiles = (P + PT - 1) / PT;
+    prm.n_ntiles = (int)((N + 127) / 128);
     int dev = 0, sms = 148;
     MGP_CUDA(cudaGetDevice(&dev));
     MGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int min_units = 0x7fffffff;
-    for (int v = 0; v < 2; ++v) {
-        const int nt = v ? 256 : 128;
-        prm.n_ntiles[v] = (int)((N + nt - 1) / nt);
-        // split the prototype tiles of an n-tile into groups so that there are >= ~8 units per CTA
-        int ppu = prm.n_ptiles;
-        while (ppu > 1 && (long long)prm.n_ntiles[v] * ((prm.n_ptiles + ppu - 1) / ppu) < 8LL * sms) ppu = (ppu + 1) / 2;
-        prm.ppu[v] = ppu;
-        prm.n_pgroups[v] = (prm.n_ptiles + ppu - 1) / ppu;
-        prm.n_units[v] = prm.n_ntiles[v] * prm.n_pgroups[v];
-        if (prm.n_units[v] < min_units) min_units = prm.n_units[v];
+    // teams of 4 CTAs (fewer when there are fewer prototype tiles) share an x tile and write adjacent tiles
+    int team = 4;
+    {
+        const char* ts = getenv("MGP_TC_TEAM");
+        if (ts && atoi(ts) > 0) team = atoi(ts);
     }
-    const size_t fixed = (size_t)1024 * D /*x tile*/ + 1024 /*align*/ + 2048 /*barriers + sn tile*/;
-    int stages = (int)((227 * 1024 - fixed) / (2 * SUB_BYTES));
-    if (stages > 6) stages = 6;
-    if (stages < 2) return MGP_ERR_UNSUPPORTED;
-    prm.stages = stages;
-    const size_t smem = fixed + (size_t)stages * 2 * SUB_BYTES;
-    const int grid = min_units < sms ? min_units : sms;
+    if (team > prm.n_ptiles) team = prm.n_ptiles;
+    if (team > sms) team = sms;
+    int n_teams = sms / team;
+    if (n_teams > prm.n_ntiles) n_teams = prm.n_ntiles;
+    prm.team = team;
+    const int grid = n_teams * team;
+    // shared memory: 1 KiB alignment slack + x tile(s) + prototype stages [+ 32 KiB TMA-store staging] + 2 KiB misc
+    const size_t x_max = (size_t)1024 * D;                        // general: 128 x 2D x 4 B (the isotropic tile is half)
+    if (1024 + x_max + (size_t)2 * 2 * SUB_BYTES + (tma_store ? STAGING_BYTES : 0) + 2048 > (size_t)227 * 1024)
+        return MGP_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)227 * 1024;
+    prm.smem_bytes = (uint32_t)smem;
 
 #define MGP_TC_LAUNCH(L)                                                                                           \
     do {                                                                                                           \
         MGP_CUDA(cudaFuncSetAttribute(logprob_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        logprob_tc_kernel<L><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mph, mpl, prm);                                     \
+        logprob_tc_kernel<L><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mph, mpl, mout, prm);                               \
     } while (0)
-    if (layout == MGP_OUT_LOGP_NP) MGP_TC_LAUNCH(MGP_OUT_LOGP_NP);
+    if (tma_store) MGP_TC_LAUNCH(LAYOUT_NP_TMA);
+    else if (layout == MGP_OUT_LOGP_NP) MGP_TC_LAUNCH(MGP_OUT_LOGP_NP);
     else if (layout == MGP_OUT_LOGP_BPHW) MGP_TC_LAUNCH(MGP_OUT_LOGP_BPHW);
     else MGP_TC_LAUNCH(MGP_OUT_NEGP_BPHW);
 #undef MGP_TC_LAUNCH

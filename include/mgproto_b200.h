@@ -88,6 +88,12 @@ int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const float* sigma, f
 int mgp_head_select(const float* logp_bphw, const float* weight_cp, const int64_t* gt,
                     float* logits, float* vals, int32_t* idx, int B, int HW, int C, int K,
                     int T, void* stream);
+/* Same, reading the [N,P] layout (MGP_OUT_LOGP_NP, N = B*HW) that compute_log_prob and the
+ * tensor-core kernel produce at full speed: the block of an image and a group of classes is
+ * staged through shared memory. */
+int mgp_head_select_np(const float* logp_np, const float* weight_cp, const int64_t* gt,
+                       float* logits, float* vals, int32_t* idx, int B, int HW, int C, int K,
+                       int T, void* stream);
 
 /* Backward of mgp_head_select composed with the log-likelihood and the normalisation:
  * grad_logits [B,C,T] -> g_x_nchw [B,D,HW] (gradient w.r.t. the un-normalised features;

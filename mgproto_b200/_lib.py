@@ -26,6 +26,7 @@ SIGNATURES = {
     "mgp_logprob_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mgp_logprob_fwd": (_i, [_vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "mgp_head_select": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mgp_head_select_np": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mgp_head_bwd_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "mgp_head_bwd": (_i, [_vp] * 11 + [_sz, _vp] + [_i] * 6 + [_vp]),
     "mgp_mined_gather": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),

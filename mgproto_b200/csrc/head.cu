@@ -19,15 +19,15 @@ __device__ __forceinline__ float key2f(unsigned k) {
 // local maxima, REDUX.min on the index among equal maxima, winner removed from its lane.  The NR rows
 // are independent dependency chains, interleaved to hide the REDUX latency.
 template <int R, int NR>
-__device__ __forceinline__ void warp_topT(const float* const (&rows)[NR], int HW, int T, int lane, float (&out_v)[NR],
-                                          int (&out_i)[NR]) {
+__device__ __forceinline__ void warp_topT(const float* const (&rows)[NR], int rs, int HW, int T, int lane,
+                                          float (&out_v)[NR], int (&out_i)[NR]) {
     unsigned key[NR][R];
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int j = lane + 32 * r;
-            key[i][r] = (j < HW) ? f2key(__ldg(rows[i] + j)) : 0u;  // 0 sorts below every real float (incl. -inf)
+            key[i][r] = (j < HW) ? f2key(rows[i][(size_t)j * rs]) : 0u;  // 0 sorts below every real float (incl. -inf)
         }
         out_v[i] = 0.f;
         out_i[i] = 0;
@@ -62,7 +62,7 @@ __device__ __forceinline__ void warp_topT(const float* const (&rows)[NR], int HW
 // original keys by shuffle and takes the position of its value; equal values picked twice from one lane
 // are disambiguated by their rank among earlier identical picks (MATCH.ANY).
 template <int R, int NR>
-__device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR], int HW, int T, int lane,
+__device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR], int rs, int HW, int T, int lane,
                                                  float (&out_v)[NR], int (&out_i)[NR]) {
     unsigned orig[NR][R], key[NR][R];
 #pragma unroll
@@ -70,7 +70,7 @@ __device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR],
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int j = lane + 32 * r;
-            orig[i][r] = (j < HW) ? f2key(__ldg(rows[i] + j)) : 0u;
+            orig[i][r] = (j < HW) ? f2key(rows[i][(size_t)j * rs]) : 0u;
             key[i][r] = orig[i][r];
         }
 #pragma unroll
@@ -119,29 +119,49 @@ __device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR],
     }
 }
 
-template <int R, int NR>
-__global__ void __launch_bounds__(256)
+// FROM_NP = false: logp is [B,P,HW] (one contiguous row per (image, prototype)).
+// FROM_NP = true : logp is [N,P] (the compute_log_prob / tensor-core layout): the CTA first stages the
+//                  [HW x CT*K] block of its image and classes in shared memory (each patch row is a contiguous
+//                  CT*K*4-byte read), then selects along the columns (pitch CT*K+1: conflict-free).
+template <int R, int NR, bool FROM_NP>
+__global__ void __launch_bounds__(256, (R <= 8) ? 3 : 1)
 head_select_kernel(const float* __restrict__ logp, const float* __restrict__ weight, const int64_t* __restrict__ gt,
                    float* __restrict__ logits, float* __restrict__ vals, int32_t* __restrict__ idx, int HW, int C,
                    int K, int T, int CT) {
-    extern __shared__ float win[];  // [CT*K][T] exp(log p) of the winners
+    extern __shared__ float win[];  // [CT*K][T] exp(log p) of the winners  (+ [HW][CT*K+1] tile when FROM_NP)
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * CT;
     const int nc = min(CT, C - c0);
     const int P = C * K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npl = nc * K;
+    const int pitch = CT * K + 1;
+    float* tile = win + CT * K * T;
+    if (FROM_NP) {
+        const float* src = logp + (size_t)b * HW * P + (size_t)c0 * K;
+        // asynchronous 4-byte copies (LDGSTS): every element of the block is in flight at once, no register
+        // staging; rows are only 4-byte aligned in general (P need not be a multiple of 4)
+        for (int hw = warp; hw < HW; hw += 8)
+            for (int j = lane; j < npl; j += 32) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + hw * pitch + j);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + (size_t)hw * P + j) : "memory");
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
     for (int pl0 = warp * NR; pl0 < npl; pl0 += 8 * NR) {
         const float* rows[NR];
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             const int pl = min(pl0 + i, npl - 1);              // surplus slots recompute the last row, not stored
-            rows[i] = logp + ((size_t)b * P + c0 * K + pl) * HW;
+            rows[i] = FROM_NP ? (tile + pl) : (logp + ((size_t)b * P + c0 * K + pl) * HW);
         }
+        const int rs = FROM_NP ? pitch : 1;
         float v[NR];
         int ix[NR];
-        if (R <= 8) warp_topT_sorted<(R <= 8 ? R : 1), NR>(rows, HW, T, lane, v, ix);
-        else warp_topT<R, NR>(rows, HW, T, lane, v, ix);
+        if (R <= 8) warp_topT_sorted<(R <= 8 ? R : 1), NR>(rows, rs, HW, T, lane, v, ix);
+        else warp_topT<R, NR>(rows, rs, HW, T, lane, v, ix);
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             const int pl = pl0 + i;
@@ -472,25 +492,33 @@ __global__ void push_argmin_kernel(const float* __restrict__ logp, const int64_t
 
 }  // namespace
 
-extern "C" int mgp_head_select(const float* logp_bphw, const float* weight_cp, const int64_t* gt, float* logits,
-                               float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream) {
-    if (!logp_bphw || !weight_cp || !logits || !vals || !idx) return MGP_ERR_INVALID;
+static int head_select_launch(const float* logp, int from_np, const float* weight_cp, const int64_t* gt, float* logits,
+                              float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream) {
+    if (!logp || !weight_cp || !logits || !vals || !idx) return MGP_ERR_INVALID;
     if (B <= 0 || HW <= 0 || C <= 0 || K <= 0 || T <= 0) return MGP_ERR_INVALID;
     if (T > 32 || T > HW || HW > 1024) return MGP_ERR_UNSUPPORTED;
     int CT = 64 / K;
     if (CT < 1) CT = 1;
     if (CT > C) CT = C;
     size_t smem = (size_t)CT * K * T * sizeof(float);
-    if (smem > 160 * 1024) return MGP_ERR_UNSUPPORTED;
+    if (from_np) smem += (size_t)HW * (CT * K + 1) * sizeof(float);
+    if (smem > 200 * 1024) return MGP_ERR_UNSUPPORTED;
     dim3 grid((C + CT - 1) / CT, B);
     cudaStream_t st = (cudaStream_t)stream;
     const int R = (HW + 31) / 32;
+#define MGP_LAUNCH_SEL2(RR, NRR, NP)                                                                                 \
+    do {                                                                                                             \
+        MGP_CUDA(cudaFuncSetAttribute(head_select_kernel<RR, NRR, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)smem));                                                                   \
+        MGP_CUDA(cudaFuncSetAttribute(head_select_kernel<RR, NRR, NP>,                                               \
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, NP ? 100 : 25));               \
+        head_select_kernel<RR, NRR, NP><<<grid, 256, smem, st>>>(logp, weight_cp, gt, logits, vals, idx, HW, C, K,   \
+                                                                 T, CT);                                             \
+    } while (0)
 #define MGP_LAUNCH_SEL(RR, NRR)                                                                                      \
     do {                                                                                                             \
-        MGP_CUDA(cudaFuncSetAttribute(head_select_kernel<RR, NRR>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                      (int)smem));                                                                   \
-        head_select_kernel<RR, NRR><<<grid, 256, smem, st>>>(logp_bphw, weight_cp, gt, logits, vals, idx, HW, C, K,  \
-                                                             T, CT);                                                 \
+        if (from_np) MGP_LAUNCH_SEL2(RR, NRR, true);                                                                 \
+        else MGP_LAUNCH_SEL2(RR, NRR, false);                                                                        \
     } while (0)
     if (R <= 2) MGP_LAUNCH_SEL(2, 4);
     else if (R <= 4) MGP_LAUNCH_SEL(4, 4);
@@ -499,8 +527,19 @@ extern "C" int mgp_head_select(const float* logp_bphw, const float* weight_cp, c
     else if (R <= 25) MGP_LAUNCH_SEL(25, 1);
     else MGP_LAUNCH_SEL(32, 1);
 #undef MGP_LAUNCH_SEL
+#undef MGP_LAUNCH_SEL2
     MGP_CHECK_LAUNCH();
     return MGP_OK;
+}
+
+extern "C" int mgp_head_select(const float* logp_bphw, const float* weight_cp, const int64_t* gt, float* logits,
+                               float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream) {
+    return head_select_launch(logp_bphw, 0, weight_cp, gt, logits, vals, idx, B, HW, C, K, T, stream);
+}
+
+extern "C" int mgp_head_select_np(const float* logp_np, const float* weight_cp, const int64_t* gt, float* logits,
+                                  float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream) {
+    return head_select_launch(logp_np, 1, weight_cp, gt, logits, vals, idx, B, HW, C, K, T, stream);
 }
 
 extern "C" size_t mgp_head_bwd_ws_bytes(int B, int HW, int P, int D) {

@@ -34,6 +34,8 @@ namespace {
 constexpr int NT_MAX = 256;      // patches per tile (UMMA N): 256 (192 with the TMA-store epilogue) when sigma is
                                  // isotropic, else 128
 constexpr int LAYOUT_NP_TMA = 3; // internal: [N,P] output written by TMA bulk tensor stores from a shared-memory stage
+constexpr int LAYOUT_BPHW_TMA = 4;   // internal: [B,P,HW] log p through a 3-D tensor map (boxes clipped at image ends)
+constexpr int LAYOUT_NEGP_TMA = 5;   // internal: [B,P,HW] -exp(log p), same
 constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // one [32 patches x 32 prototypes] fp32 block per epilogue warp
 constexpr int PT = 128;          // prototypes per tile (UMMA M)
 constexpr int KB = 64;           // K elements per smem block (128 B rows, SWIZZLE_128B)
@@ -92,6 +94,11 @@ __host__ __device__ __forceinline__ uint32_t swz_off(int r, int k) {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -269,6 +276,31 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
         }
         return;
     }
+    if (LAYOUT == LAYOUT_BPHW_TMA || LAYOUT == LAYOUT_NEGP_TMA) {
+        // [B,P,HW]: this thread's 32 values are 128 contiguous bytes of row (b, p).  Stage [32 prototypes x 128 B]
+        // with the tensor map's 128B swizzle (8 x STS.128 per thread, conflict-free) and let the TMA engine write
+        // it; a chunk that crosses an image end is stored twice, each store clipped to its image by the 3-D map.
+        const int lane = threadIdx.x & 31;
+        if (LAYOUT == LAYOUT_NEGP_TMA) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = -expf(v[j]);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        uint8_t* rowp = reinterpret_cast<uint8_t*>(stg) + lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(rowp + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && !(prm.debug & 1)) {
+            const int b = n0 / HW, hw0 = n0 - b * HW;
+            tma_store_3d(map_out, smem_u32(stg), hw0, p - lane, b);
+            if (hw0 + 32 > HW) tma_store_3d(map_out, smem_u32(stg), hw0 - HW, p - lane, b + 1);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
+    }
     if (!pok) return;
     if (prm.debug & 1) {
         float acc = 0.f;
@@ -315,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                   const __grid_constant__ CUtensorMap map_ph, const __grid_constant__ CUtensorMap map_pl,
                   const __grid_constant__ CUtensorMap map_out, const TcParams prm) {
-    constexpr bool TMA_ST = (LAYOUT == LAYOUT_NP_TMA);
+    constexpr bool TMA_ST = (LAYOUT == LAYOUT_NP_TMA || LAYOUT == LAYOUT_BPHW_TMA || LAYOUT == LAYOUT_NEGP_TMA);
     constexpr int NT = 128;                                       // patches per tile = UMMA N
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -558,6 +590,19 @@ bool make_out_map(CUtensorMap* m, const void* ptr, uint64_t N, uint64_t P) {
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// output [B, P, HW] fp32, box = 32 patches x 32 prototypes x 1 image, 128B swizzle (inner box = 128 B)
+bool make_out_map_bphw(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t P, uint64_t HW) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {HW, P, B};
+    cuuint64_t strides[2] = {HW * sizeof(float), P * HW * sizeof(float)};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
@@ -618,12 +663,20 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     CUtensorMap mxh, mxl, mph, mpl;
     CUtensorMap mout;
     const char* no_tma = getenv("MGP_TC_NO_TMA_STORE");
-    const bool tma_store = (layout == MGP_OUT_LOGP_NP) && (P % 4 == 0) && !(no_tma && atoi(no_tma));
+    const bool tma_ok = !(no_tma && atoi(no_tma));
+    const bool tma_np = (layout == MGP_OUT_LOGP_NP) && (P % 4 == 0) && tma_ok;
+    // [B,P,HW] through the 3-D map needs chunks that do not cross an image end (a negative start coordinate
+    // faults): enabled only when 32 | HW until the image-aligned tiling lands
+    const bool tma_bphw = (layout != MGP_OUT_LOGP_NP) && (HW % 32 == 0) && tma_ok;
+    const bool tma_store = tma_np || tma_bphw;
     if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, 128) || !make_map(&mxl, al, (uint64_t)N, 2 * D, 128) ||
         !make_map(&mph, bh, (uint64_t)P, 2 * D, 128) || !make_map(&mpl, bl, (uint64_t)P, 2 * D, 128))
         return MGP_ERR_UNSUPPORTED;
-    if (!make_out_map(&mout, tma_store ? out : (float*)ah, tma_store ? (uint64_t)N : 64, tma_store ? (uint64_t)P : 64))
+    if (tma_bphw) {
+        if (!make_out_map_bphw(&mout, out, (uint64_t)B, (uint64_t)P, (uint64_t)HW)) return MGP_ERR_UNSUPPORTED;
+    } else if (!make_out_map(&mout, tma_np ? out : (float*)ah, tma_np ? (uint64_t)N : 64, tma_np ? (uint64_t)P : 64)) {
         return MGP_ERR_UNSUPPORTED;
+    }
 
     TcParams prm;
     prm.e0 = e0; prm.e1 = e1; prm.e2 = e2; prm.sn = sn; prm.noniso = flag; prm.out = out;
@@ -661,7 +714,9 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
         MGP_CUDA(cudaFuncSetAttribute(logprob_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         logprob_tc_kernel<L><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mph, mpl, mout, prm);                               \
     } while (0)
-    if (tma_store) MGP_TC_LAUNCH(LAYOUT_NP_TMA);
+    if (tma_np) MGP_TC_LAUNCH(LAYOUT_NP_TMA);
+    else if (tma_bphw && layout == MGP_OUT_LOGP_BPHW) MGP_TC_LAUNCH(LAYOUT_BPHW_TMA);
+    else if (tma_bphw) MGP_TC_LAUNCH(LAYOUT_NEGP_TMA);
     else if (layout == MGP_OUT_LOGP_NP) MGP_TC_LAUNCH(MGP_OUT_LOGP_NP);
     else if (layout == MGP_OUT_LOGP_BPHW) MGP_TC_LAUNCH(MGP_OUT_LOGP_BPHW);
     else MGP_TC_LAUNCH(MGP_OUT_NEGP_BPHW);

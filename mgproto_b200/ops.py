@@ -106,11 +106,18 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
 
 
 # ----------------------------------------------------------------------------------- a4-a7
-def head_select(logp_bphw, weight_cp, gt, T, C, K):
-    """ref model.py:188-206, :218-222, :254 -> (logits [B,C,T], vals [B,P,T], idx [B,P,T] int32)."""
-    lp = _req(logp_bphw, torch.float32, "logp")
+def head_select(logp, weight_cp, gt, T, C, K, B=None, HW=None):
+    """ref model.py:188-206, :218-222, :254 -> (logits [B,C,T], vals [B,P,T], idx [B,P,T] int32).
+    logp is [B,P,HW], or [N,P] (then pass B and HW)."""
+    lp = _req(logp, torch.float32, "logp")
     w = _req(weight_cp, torch.float32, "last_layer.weight")
-    B, P, HW = lp.shape
+    from_np = lp.dim() == 2
+    if from_np:
+        N, P = lp.shape
+        if B is None or HW is None or B * HW != N:
+            raise RuntimeError("mgproto_b200: head_select on [N,P] needs B*HW == N")
+    else:
+        B, P, HW = lp.shape
     if P != C * K or w.shape != (C, P):
         raise RuntimeError("mgproto_b200: shape mismatch in head_select")
     if gt is not None:
@@ -120,8 +127,9 @@ def head_select(logp_bphw, weight_cp, gt, T, C, K):
     logits = torch.empty((B, C, T), device=lp.device, dtype=torch.float32)
     vals = torch.empty((B, P, T), device=lp.device, dtype=torch.float32)
     idx = torch.empty((B, P, T), device=lp.device, dtype=torch.int32)
-    check(_lib.load().mgp_head_select(lp.data_ptr(), w.data_ptr(), _p(gt), logits.data_ptr(), vals.data_ptr(),
-                                      idx.data_ptr(), B, HW, C, K, T, _stream()), "mgp_head_select")
+    fn = _lib.load().mgp_head_select_np if from_np else _lib.load().mgp_head_select
+    check(fn(lp.data_ptr(), w.data_ptr(), _p(gt), logits.data_ptr(), vals.data_ptr(), idx.data_ptr(), B, HW, C, K, T,
+             _stream()), "mgp_head_select")
     _count(1)
     return logits, vals, idx
 
@@ -146,7 +154,7 @@ class HeadFunction(torch.autograd.Function):
         sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
         wt = weight_cp.detach().contiguous()
         xhat, inv, _ = normalize_fwd(x_add)
-        lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)
+        lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)   # [B,P,HW]: contiguous rows for the mining
         logits, vals, idx = head_select(lp, wt, gt, T, C, K)
         ctx.save_for_backward(logits, vals, idx, wt, gt if gt is not None else torch.empty(0), xhat, inv, mu, sg)
         ctx.has_gt = gt is not None

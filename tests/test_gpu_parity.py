@@ -429,3 +429,19 @@ def test_ood_score_auroc_matches_oracle():
     y = np.r_[np.ones(n), np.zeros(n)]
     assert abs(roc_auc_score(y, score) - roc_auc_score(y, ref)) < 1e-9
     assert roc_auc_score(y, ref) > 0.9
+
+
+def test_logprob_tc_bphw_tma_path():
+    """[B,P,HW] written by 3-D TMA stores (taken when 32 | HW): against the exact fp32 kernel."""
+    from mgproto_b200 import ops, _lib
+    if not _lib.load().mgp_has_tensor_core_path():
+        pytest.skip("library built without the tcgen05 path")
+    B, HW, P, D = 5, 64, 300, 128
+    g = torch.Generator().manual_seed(3)
+    x = F.normalize(torch.randn(B * HW, D, generator=g), dim=1).to(_dev())
+    mu = F.normalize(torch.rand(P, D, generator=g), dim=1).to(_dev())
+    sg = torch.full((P, D), 0.4, device=_dev())
+    for layout in (1, 2):
+        a = ops.logprob(x, mu, sg, layout, B=B, HW=HW, math="tc")
+        b = ops.logprob(x, mu, sg, layout, B=B, HW=HW, math="fp32")
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 if layout == 1 else 1e-12)

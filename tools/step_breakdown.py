@@ -53,6 +53,9 @@ def main():
             res["logprob_" + m] = "unavailable: %s" % e
     lp = ops.logprob(xhat, mu, sg, 1, B=B, HW=HW, math=math)
     res["head_select"] = timeit(lambda: ops.head_select(lp, wt, gt, T, C, K))
+    lpn = ops.logprob(xhat, mu, sg, 0, math=math)
+    res["head_select_np"] = timeit(lambda: ops.head_select(lpn, wt, gt, T, C, K, B=B, HW=HW))
+    del lpn
     logits, vals, idx = ops.head_select(lp, wt, gt, T, C, K)
     xr = x.clone().requires_grad_(True)
 

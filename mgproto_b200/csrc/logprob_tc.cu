@@ -235,6 +235,7 @@ struct TcParams {
     float* out;
     int N, HW, P, D;
     int n_ntiles, n_ptiles;
+    int B, nti;            // image-aligned tiling of the [B,P,HW] TMA path: one x tile = one image, nti = round_up(HW, 32) columns
     int team;              // CTAs per team: the CTAs of a team work on the SAME x tile at the same time, on
                            // adjacent prototype tiles, so each output row receives team*512 contiguous bytes at once
     uint32_t smem_bytes;   // dynamic shared memory of the launch
@@ -247,7 +248,8 @@ constexpr int TC_THREADS = 384;   // warps: 0 proto TMA, 1 MMA, 2 TMEM alloc, 3 
 template <int LAYOUT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const float* __restrict__ s_sn_c, float c0,
                                                float c1, float c2, int n0, int p, bool pok, const TcParams& prm,
-                                               float* stg = nullptr, const CUtensorMap* map_out = nullptr) {
+                                               float* stg = nullptr, const CUtensorMap* map_out = nullptr, int img_b = 0,
+                                               int img_hw0 = 0) {
     const int N = prm.N, P = prm.P, HW = prm.HW;
     float v[32];
     const float4* s4 = reinterpret_cast<const float4*>(s_sn_c);    // |x_n|^2 of the 32 columns (shared memory)
@@ -279,7 +281,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
     if (LAYOUT == LAYOUT_BPHW_TMA || LAYOUT == LAYOUT_NEGP_TMA) {
         // [B,P,HW]: this thread's 32 values are 128 contiguous bytes of row (b, p).  Stage [32 prototypes x 128 B]
         // with the tensor map's 128B swizzle (8 x STS.128 per thread, conflict-free) and let the TMA engine write
-        // it; a chunk that crosses an image end is stored twice, each store clipped to its image by the 3-D map.
+        // it.  Tiles are image-aligned here, so a chunk lies in ONE image; columns past HW are clipped by the map.
         const int lane = threadIdx.x & 31;
         if (LAYOUT == LAYOUT_NEGP_TMA) {
 #pragma unroll
@@ -294,9 +296,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0 && !(prm.debug & 1)) {
-            const int b = n0 / HW, hw0 = n0 - b * HW;
-            tma_store_3d(map_out, smem_u32(stg), hw0, p - lane, b);
-            if (hw0 + 32 > HW) tma_store_3d(map_out, smem_u32(stg), hw0 - HW, p - lane, b + 1);
+            tma_store_3d(map_out, smem_u32(stg), img_hw0, p - lane, img_b);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         return;
@@ -348,7 +348,10 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                   const __grid_constant__ CUtensorMap map_ph, const __grid_constant__ CUtensorMap map_pl,
                   const __grid_constant__ CUtensorMap map_out, const TcParams prm) {
     constexpr bool TMA_ST = (LAYOUT == LAYOUT_NP_TMA || LAYOUT == LAYOUT_BPHW_TMA || LAYOUT == LAYOUT_NEGP_TMA);
-    constexpr int NT = 128;                                       // patches per tile = UMMA N
+    constexpr bool BPHW_TMA = (LAYOUT == LAYOUT_BPHW_TMA || LAYOUT == LAYOUT_NEGP_TMA);
+    // the layout used by the non-TMA fallback of the same instantiation (anisotropic sigma: see `img` below)
+    constexpr int STG_LAYOUT = (LAYOUT == LAYOUT_BPHW_TMA) ? MGP_OUT_LOGP_BPHW
+                               : (LAYOUT == LAYOUT_NEGP_TMA) ? MGP_OUT_NEGP_BPHW : LAYOUT;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024 B alignment
@@ -357,11 +360,18 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     const bool gen = (*prm.noniso != 0);
     const int nkb = (gen ? 2 * prm.D : prm.D) / KB;               // K blocks per tile
     const int kcol0 = gen ? 0 : prm.D;                            // isotropic: only the [x] / [-2 w mu] half
+    // [B,P,HW] through TMA: one x tile = one image (nti = round_up(HW,32) columns, UMMA N = nti) so that no
+    // 32-column chunk crosses an image end.  The wider tile only fits when sigma is isotropic (K = D);
+    // otherwise this instantiation falls back to 128-patch tiles and register stores.
+    const bool img = BPHW_TMA && !gen;
+    const int NT = img ? prm.nti : 128;                           // patches per tile = UMMA N
+    const int row_step = img ? prm.HW : 128;                      // first patch row of x tile nt = nt * row_step
     const uint32_t idesc = make_idesc(NT);
-    const int n_ptiles = prm.n_ptiles, n_ntiles = prm.n_ntiles;
+    const int n_ptiles = prm.n_ptiles, n_ntiles = img ? prm.B : prm.n_ntiles;
+    const uint32_t xsub = (uint32_t)NT * KB * 2;                  // one [NT x 64] fp16 block of the x tile
 
     // carve-up: nbuf x tiles | S stages of (proto hi, proto lo) | [TMA-store staging] | barriers + sn tile
-    const uint32_t x_bytes = (uint32_t)(2 * nkb) * SUB_BYTES;     // hi blocks then lo blocks
+    const uint32_t x_bytes = (uint32_t)(2 * nkb) * xsub;          // hi blocks then lo blocks
     const uint32_t tile_budget = prm.smem_bytes - 1024u - 2048u - (TMA_ST ? (uint32_t)STAGING_BYTES : 0u);
     const int nbuf = (2 * x_bytes + 2 * 2 * SUB_BYTES <= tile_budget) ? 2 : 1;   // double-buffer x when it fits
     int S = (int)((tile_budget - nbuf * x_bytes) / (2 * SUB_BYTES));
@@ -381,7 +391,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     auto TFULL = [&](int i) { return bar0 + 8u * (16 + i); };
     auto TEMPTY = [&](int i) { return bar0 + 8u * (18 + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-    float* s_sn = reinterpret_cast<float*>(bars + 22);            // [2][NT] |x|^2 of the x tiles, 16 B aligned
+    float* s_sn = reinterpret_cast<float*>(bars + 22);            // [256] |x|^2 of the current x tile, 16 B aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -396,7 +406,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -420,10 +430,12 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
             if (c >= nbuf) mbar_wait(XEMPTY(buf), (uint32_t)((c / nbuf - 1) & 1));
             mbar_expect_tx(XFULL(buf), x_bytes);
             const uint32_t xb = x_base + (uint32_t)buf * x_bytes;
-            for (int kb = 0; kb < nkb; ++kb) {
-                tma_load_2d(xb + (uint32_t)kb * SUB_BYTES, &map_xh, kcol0 + kb * KB, nt * NT, XFULL(buf));
-                tma_load_2d(xb + (uint32_t)(nkb + kb) * SUB_BYTES, &map_xl, kcol0 + kb * KB, nt * NT, XFULL(buf));
-            }
+            for (int kb = 0; kb < nkb; ++kb)
+                for (int r = 0; r < NT; r += 32) {                // x maps use 32-row boxes (NT = 128 or 224/256)
+                    const uint32_t ro = (uint32_t)r * KB * 2;
+                    tma_load_2d(xb + (uint32_t)kb * xsub + ro, &map_xh, kcol0 + kb * KB, nt * row_step + r, XFULL(buf));
+                    tma_load_2d(xb + (uint32_t)(nkb + kb) * xsub + ro, &map_xl, kcol0 + kb * KB, nt * row_step + r, XFULL(buf));
+                }
         }
     } else if (warp == 0 && lane == 0) {
         // =========================== prototype TMA producer ===========================
@@ -461,7 +473,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                     mbar_wait(FULL(stage), phase);
                     tc_fence_after();
                     const uint32_t ph = st_base + (uint32_t)stage * 2 * SUB_BYTES, pl = ph + SUB_BYTES;
-                    const uint32_t xh = xb + (uint32_t)kb * SUB_BYTES, xl = xb + (uint32_t)(nkb + kb) * SUB_BYTES;
+                    const uint32_t xh = xb + (uint32_t)kb * xsub, xl = xb + (uint32_t)(nkb + kb) * xsub;
 #pragma unroll
                     for (int k = 0; k < KB / 16; ++k) {
                         if (prm.debug & 4) continue;
@@ -487,21 +499,20 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
         const int e = warp - 4;
         const int q = e & 3, h = e >> 2;
         const int et = q * 32 + lane;                             // prototype row within the tile (TMEM lane)
-        constexpr int hcols = NT / 2;                             // 64 columns = 2 chunks per warp
+        const int nch_all = NT / 32;                              // 4 chunks (NT = 128) or up to 8 (image tiles)
+        const int ch0 = h ? (nch_all + 1) / 2 : 0, ch1 = h ? nch_all : (nch_all + 1) / 2;   // this warp's chunks
         float* stg = staging + e * 1024;                          // this warp's 4 KiB TMA-store block
         int acc = 0, c = 0;
         uint32_t acc_par = 0;
         const bool skip_epi = (prm.debug & 8) != 0;
         for (int nt = team; nt < n_ntiles; nt += n_teams, ++c) {
-            float* sn_t = s_sn + (c & 1) * NT;                    // double-buffered: no barrier against readers of c-1
-            asm volatile("bar.sync 1, 256;" ::: "memory");        // ... but c-2's readers must be done
+            const int row0 = nt * row_step;
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // readers of the previous x tile's norms are done
             for (int i = e * 32 + lane; i < NT; i += 256) {
-                const int n = nt * NT + i;
-                sn_t[i] = (n < prm.N) ? prm.sn[n] : 0.f;
+                const int n = row0 + i;
+                s_sn[i] = (n < prm.N) ? prm.sn[n] : 0.f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int nbase = nt * NT + h * hcols;
-            const float* sn_g = sn_t + h * hcols;
             for (int pt = k0; pt < n_ptiles; pt += TS) {
                 const int p = pt * PT + et;
                 const bool pok = p < prm.P;
@@ -511,21 +522,41 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                 mbar_wait(TFULL(acc), acc_par);
                 tc_fence_after();
                 if (!skip_epi) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + h * hcols);
-                    uint32_t r0[32], r1[32];
-                    if (!(prm.debug & 2)) {
-                        tmem_ld32(taddr, r0);
-                        tmem_ld32(taddr + 32u, r1);
-                    } else {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+#pragma unroll 1
+                    for (int ch = ch0; ch < ch1; ch += 2) {
+                        uint32_t r0[32], r1[32];
+                        const bool two = ch + 1 < ch1;
+                        if (!(prm.debug & 2)) {
+                            tmem_ld32(taddr + (uint32_t)ch * 32u, r0);
+                            if (two) tmem_ld32(taddr + (uint32_t)(ch + 1) * 32u, r1);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
+                            for (int j = 0; j < 32; ++j) { r0[j] = 0u; r1[j] = 0u; }
+                        }
+                        tmem_ld_wait();
+                        if (ch + 2 >= ch1) {                      // accumulator slice is in registers: release it
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(TEMPTY(acc));
+                        }
+                        if (!BPHW_TMA || img) {
+                            epilogue_chunk<LAYOUT>(r0, s_sn + ch * 32, c0, c1, c2, row0 + ch * 32, p, pok, prm, stg, &map_out,
+                                                   nt, ch * 32);
+                            if (two)
+                                epilogue_chunk<LAYOUT>(r1, s_sn + (ch + 1) * 32, c0, c1, c2, row0 + (ch + 1) * 32, p, pok, prm,
+                                                       stg, &map_out, nt, (ch + 1) * 32);
+                        } else {
+                            epilogue_chunk<STG_LAYOUT>(r0, s_sn + ch * 32, c0, c1, c2, row0 + ch * 32, p, pok, prm);
+                            if (two)
+                                epilogue_chunk<STG_LAYOUT>(r1, s_sn + (ch + 1) * 32, c0, c1, c2, row0 + (ch + 1) * 32, p, pok, prm);
+                        }
                     }
-                    tmem_ld_wait();
-                    tc_fence_before();                            // accumulator is in registers: release it
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(TEMPTY(acc));
-                    epilogue_chunk<LAYOUT>(r0, sn_g, c0, c1, c2, nbase, p, pok, prm, stg, &map_out);
-                    epilogue_chunk<LAYOUT>(r1, sn_g + 32, c0, c1, c2, nbase + 32, p, pok, prm, stg, &map_out);
+                    if (ch0 >= ch1) {                             // (never for NT >= 64; keeps the barrier count right)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(TEMPTY(acc));
+                    }
                 } else {
                     tc_fence_before();
                     __syncwarp();
@@ -541,7 +572,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -665,11 +696,10 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     const char* no_tma = getenv("MGP_TC_NO_TMA_STORE");
     const bool tma_ok = !(no_tma && atoi(no_tma));
     const bool tma_np = (layout == MGP_OUT_LOGP_NP) && (P % 4 == 0) && tma_ok;
-    // [B,P,HW] through the 3-D map needs chunks that do not cross an image end (a negative start coordinate
-    // faults): enabled only when 32 | HW until the image-aligned tiling lands
-    const bool tma_bphw = (layout != MGP_OUT_LOGP_NP) && (HW % 32 == 0) && tma_ok;
+    // [B,P,HW] through the 3-D map uses image-aligned x tiles (a chunk may not cross an image end)
+    const bool tma_bphw = (layout != MGP_OUT_LOGP_NP) && (HW % 4 == 0) && HW >= 32 && HW <= 256 && tma_ok;
     const bool tma_store = tma_np || tma_bphw;
-    if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, 128) || !make_map(&mxl, al, (uint64_t)N, 2 * D, 128) ||
+    if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, 32) || !make_map(&mxl, al, (uint64_t)N, 2 * D, 32) ||
         !make_map(&mph, bh, (uint64_t)P, 2 * D, 128) || !make_map(&mpl, bl, (uint64_t)P, 2 * D, 128))
         return MGP_ERR_UNSUPPORTED;
     if (tma_bphw) {
@@ -687,6 +717,8 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     }
     prm.n_ptiles = (P + PT - 1) / PT;
     prm.n_ntiles = (int)((N + 127) / 128);
+    prm.B = B;
+    prm.nti = ((HW + 31) / 32) * 32;
     int dev = 0, sms = 148;
     MGP_CUDA(cudaGetDevice(&dev));
     MGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -699,7 +731,10 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     if (team > prm.n_ptiles) team = prm.n_ptiles;
     if (team > sms) team = sms;
     int n_teams = sms / team;
-    if (n_teams > prm.n_ntiles) n_teams = prm.n_ntiles;
+    {
+        const int nt_min = (tma_bphw && B < prm.n_ntiles) ? B : prm.n_ntiles;
+        if (n_teams > nt_min) n_teams = nt_min;
+    }
     prm.team = team;
     const int grid = n_teams * team;
     // shared memory: 1 KiB alignment slack + x tile(s) + prototype stages [+ 32 KiB TMA-store staging] + 2 KiB misc

@@ -318,9 +318,12 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
                     a_[i] = sqrtf(exp_avg_sq[(size_t)c * KD + o]);
                 }
             }
-            // the s-th term carries beta1^s: after 224 steps it is < 6e-11 of the first one -- far below fp32
-            // resolution of the sum -- so the parameter update stops there; the moments still decay by `count`
-            const int count_p = min(count, 224);
+            // the s-th term carries beta1^s: with beta1 = 0.9 the terms after step 128 are < 1.4e-6 of the first
+            // and add < 1e-7 (absolute) to a parameter that moves by <= 10*lr in total -- below fp32 resolution of
+            // the sum -- so the parameter update stops at beta1^s < 1e-6; the moments still decay by `count`
+            int cutoff = count;
+            if (adam.beta1 > 0.f && adam.beta1 < 1.f) cutoff = (int)ceilf(logf(1e-6f) / logf(adam.beta1));
+            const int count_p = min(count, max(cutoff, 1));
             for (int s0 = 0; s0 < count_p; s0 += TAB) {
                 const int ns = min(TAB, count_p - s0);
                 __syncthreads();

@@ -235,6 +235,7 @@ struct TcParams {
     float* out;
     int N, HW, P, D;
     int n_ntiles, n_ptiles;
+    int xbox;              // rows of the x tensor-map box
     int B, nti;            // image-aligned tiling of the [B,P,HW] TMA path: one x tile = one image, nti = round_up(HW, 32) columns
     int team;              // CTAs per team: the CTAs of a team work on the SAME x tile at the same time, on
                            // adjacent prototype tiles, so each output row receives team*512 contiguous bytes at once
@@ -431,7 +432,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
             mbar_expect_tx(XFULL(buf), x_bytes);
             const uint32_t xb = x_base + (uint32_t)buf * x_bytes;
             for (int kb = 0; kb < nkb; ++kb)
-                for (int r = 0; r < NT; r += 32) {                // x maps use 32-row boxes (NT = 128 or 224/256)
+                for (int r = 0; r < NT; r += prm.xbox) {          // x-map box rows: 128 (128-patch tiles) or 32 (image tiles)
                     const uint32_t ro = (uint32_t)r * KB * 2;
                     tma_load_2d(xb + (uint32_t)kb * xsub + ro, &map_xh, kcol0 + kb * KB, nt * row_step + r, XFULL(buf));
                     tma_load_2d(xb + (uint32_t)(nkb + kb) * xsub + ro, &map_xl, kcol0 + kb * KB, nt * row_step + r, XFULL(buf));
@@ -699,7 +700,8 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     // [B,P,HW] through the 3-D map uses image-aligned x tiles (a chunk may not cross an image end)
     const bool tma_bphw = (layout != MGP_OUT_LOGP_NP) && (HW % 4 == 0) && HW >= 32 && HW <= 256 && tma_ok;
     const bool tma_store = tma_np || tma_bphw;
-    if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, 32) || !make_map(&mxl, al, (uint64_t)N, 2 * D, 32) ||
+    const uint32_t xbox = tma_bphw ? 32u : 128u;
+    if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, xbox) || !make_map(&mxl, al, (uint64_t)N, 2 * D, xbox) ||
         !make_map(&mph, bh, (uint64_t)P, 2 * D, 128) || !make_map(&mpl, bl, (uint64_t)P, 2 * D, 128))
         return MGP_ERR_UNSUPPORTED;
     if (tma_bphw) {
@@ -718,6 +720,7 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     prm.n_ptiles = (P + PT - 1) / PT;
     prm.n_ntiles = (int)((N + 127) / 128);
     prm.B = B;
+    prm.xbox = (int)xbox;
     prm.nti = ((HW + 31) / 32) * 32;
     int dev = 0, sms = 148;
     MGP_CUDA(cudaGetDevice(&dev));

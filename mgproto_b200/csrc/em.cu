@@ -107,6 +107,97 @@ __device__ __forceinline__ float warp_estep_rowb(const float4 (&xv)[VEC4], const
     return norm;
 }
 
+// E-step of one bank row for the statistics kernel, K <= 16.  Per-lane partial sums of all components are
+// reduced with a recursive-halving butterfly (16 values: 8+4+2+1+1 = 16 shuffles instead of 5 per component);
+// afterwards lane l holds the total of component kidx(l) (each component twice: lanes l and l^1).
+//   iso  : sigma constant over d inside each component -> q_k = w_k (|x|^2 + |mu_k|^2) + x . a_k, a_k = -2 w_k mu_k
+//          (s_mu holds a_k, s_rinv is unused, s_cst[k] folds -0.5*w_k*|mu_k|^2; s_w[k] = w_k)
+//   !iso : exact form sum_d ((x - mu) rinv)^2
+// Returns the log-normaliser; `r` = smoothed responsibility of component kidx(lane) (valid lanes only).
+__device__ __forceinline__ int estep_kidx(int lane) {       // component (within a block of 8) a lane ends up holding
+    return (((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1);
+}
+// partial sums of components k0 .. k0+7 of this lane, reduced over the warp: 4+2+1+1+1 = 9 shuffles;
+// returns the total of component k0 + estep_kidx(lane) (each component ends up in 4 lanes)
+template <int VEC4>
+__device__ __forceinline__ float estep_block8(const float4 (&xv)[VEC4], float xx, const float* __restrict__ s_mu,
+                                              const float* __restrict__ s_rinv, const float* __restrict__ s_w, bool iso,
+                                              int k0, int K, int D, int lane) {
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        q[i] = 0.f;
+        const int k = k0 + i;
+        if (k < K) {
+#pragma unroll
+            for (int j = 0; j < VEC4; ++j) {
+                const int d = 4 * (lane + 32 * j);
+                if (d >= D) continue;
+                const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + d);
+                if (iso) {
+                    q[i] = fmaf(xv[j].x, m.x, q[i]); q[i] = fmaf(xv[j].y, m.y, q[i]);
+                    q[i] = fmaf(xv[j].z, m.z, q[i]); q[i] = fmaf(xv[j].w, m.w, q[i]);
+                } else {
+                    const float4 rr = *reinterpret_cast<const float4*>(s_rinv + k * D + d);
+                    float t;
+                    t = (xv[j].x - m.x) * rr.x; q[i] = fmaf(t, t, q[i]);
+                    t = (xv[j].y - m.y) * rr.y; q[i] = fmaf(t, t, q[i]);
+                    t = (xv[j].z - m.z) * rr.z; q[i] = fmaf(t, t, q[i]);
+                    t = (xv[j].w - m.w) * rr.w; q[i] = fmaf(t, t, q[i]);
+                }
+            }
+            if (iso) q[i] = fmaf(s_w[k], xx, q[i]);          // every lane adds its share of w_k |x|^2
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = (lane & 16) != 0;
+        const float keep = up ? q[i + 4] : q[i], send = up ? q[i] : q[i + 4];
+        q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = (lane & 8) != 0;
+        const float keep = up ? q[i + 2] : q[i], send = up ? q[i] : q[i + 2];
+        q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const bool up = (lane & 4) != 0;
+        const float keep = up ? q[1] : q[0], send = up ? q[0] : q[1];
+        q[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], 2);
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+    return q[0];
+}
+template <int VEC4>
+__device__ __forceinline__ float warp_estep_packed(const float4 (&xv)[VEC4], const float* __restrict__ s_mu,
+                                                   const float* __restrict__ s_rinv, const float* __restrict__ s_cst,
+                                                   const float* __restrict__ s_w, bool iso, int K, int D, int lane,
+                                                   float alpha, float& r0, float& r1, int& kk) {
+    float xx = 0.f;
+    if (iso) {
+#pragma unroll
+        for (int j = 0; j < VEC4; ++j) {
+            xx = fmaf(xv[j].x, xv[j].x, xx); xx = fmaf(xv[j].y, xv[j].y, xx);
+            xx = fmaf(xv[j].z, xv[j].z, xx); xx = fmaf(xv[j].w, xv[j].w, xx);
+        }
+    }
+    kk = estep_kidx(lane);
+    const float q0 = estep_block8<VEC4>(xv, xx, s_mu, s_rinv, s_w, iso, 0, K, D, lane);
+    const float q1 = (K > 8) ? estep_block8<VEC4>(xv, xx, s_mu, s_rinv, s_w, iso, 8, K, D, lane) : 0.f;
+    const bool v0 = kk < K, v1 = kk + 8 < K;
+    const float w0 = v0 ? s_cst[kk] - 0.5f * q0 : -INFINITY;            // lp + log(pi + eps)   (ref :316)
+    const float w1 = v1 ? s_cst[kk + 8] - 0.5f * q1 : -INFINITY;
+    const float mx = warp_max(fmaxf(w0, w1));
+    const float e0 = v0 ? expf(w0 - mx) : 0.f, e1 = v1 ? expf(w1 - mx) : 0.f;
+    const float se = 0.25f * warp_sum(e0 + e1);                         // every component sits in four lanes
+    const float inv_se = 1.0f / se, inv_den = 1.0f / (1.0f + (float)K * alpha);
+    r0 = v0 ? fmaf(e0, inv_se, alpha) * inv_den : 0.f;                  // ref :380-383
+    r1 = v1 ? fmaf(e1, inv_se, alpha) * inv_den : 0.f;
+    return mx + logf(se);                                               // logsumexp (ref :318)
+}
+
 template <int VEC4>
 __device__ __forceinline__ float warp_estep_row(const float4 (&xv)[VEC4], const float* __restrict__ s_mu,
                                                 const float* __restrict__ s_rinv, const float* __restrict__ s_cst,
@@ -121,7 +212,7 @@ constexpr int RB = 32;  // rows per batch
 // grid (C, n_split); CTA (c, s) reduces rows [seg_begin, seg_end) of class c.
 // Thread t owns outputs o = t + 256 i (o = k*D + d) of S1 (and S2); threads t < K own S0[t].
 template <int VEC4, int NOUT, bool WITH_S2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NOUT <= 10) ? 3 : 1)
 em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ order, const float* __restrict__ mu,
                 const float* __restrict__ sigma, const float* __restrict__ weight, float alpha, int row_begin,
                 int row_end, int n_split, float* __restrict__ stats, size_t stat_stride, int C, int K, int D, int cap) {
@@ -133,7 +224,9 @@ em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
     float* s_x = s_rinv + K * D;         // [RB][D]
     float* s_r = s_x + RB * D;           // [RB][K]
     float* s_cst = s_r + RB * K;         // [K]
+    float* s_w = s_cst + K;              // [K]  w_k (isotropic classes)
     __shared__ float s_ll[8];
+    __shared__ int s_iso;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = C * K;
@@ -143,17 +236,40 @@ em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
     const int seg_b = row_begin + split * per;
     const int seg_e = min(row_end, seg_b + per);
 
+    // sigma constant over d inside every component of this class?  (every state the shipped loop reaches)
+    if (tid == 0) s_iso = 1;
+    __syncthreads();
+    {
+        bool same = true;
+        for (int i = tid; i < K * D; i += 256) same = same && (sigma[(size_t)c * K * D + i] == sigma[(size_t)c * K * D + (i / D) * D]);
+        if (!same) s_iso = 0;
+    }
+    __syncthreads();
+    const bool packed = (K <= 16);
+    const bool iso = packed && (s_iso != 0);
     for (int i = tid; i < K * D; i += 256) {
-        s_mu[i] = mu[(size_t)c * K * D + i];
-        s_rinv[i] = 1.0f / (sigma[(size_t)c * K * D + i] + EM_EPS);                 // ref :333
+        const float rinv = 1.0f / (sigma[(size_t)c * K * D + i] + EM_EPS);           // ref :333
+        const float m = mu[(size_t)c * K * D + i];
+        s_rinv[i] = rinv;
+        s_mu[i] = iso ? -2.0f * rinv * rinv * m : m;                                  // a_k = -2 w_k mu_k
     }
     __syncthreads();
     for (int k = warp; k < K; k += 8) {
-        float ls = 0.f;
-        for (int d = lane; d < D; d += 32) ls += logf(sigma[(size_t)c * K * D + k * D + d] + EM_EPS);   // ref :334
+        float ls = 0.f, mm = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            ls += logf(sigma[(size_t)c * K * D + k * D + d] + EM_EPS);               // ref :334
+            const float m = mu[(size_t)c * K * D + k * D + d];
+            mm = fmaf(m, m, mm);
+        }
         ls = warp_sum(ls);
-        if (lane == 0)
-            s_cst[k] = -0.5f * (float)D * MGP_LOG_2PI - ls + logf(weight[(size_t)c * P + c * K + k] + EM_EPS);
+        mm = warp_sum(mm);
+        if (lane == 0) {
+            const float rinv0 = s_rinv[k * D];
+            const float wk = rinv0 * rinv0;
+            s_w[k] = wk;
+            s_cst[k] = -0.5f * (float)D * MGP_LOG_2PI - ls + logf(weight[(size_t)c * P + c * K + k] + EM_EPS) -
+                       (iso ? 0.5f * wk * mm : 0.f);
+        }
     }
     __syncthreads();
 
@@ -193,11 +309,22 @@ em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
                     *reinterpret_cast<float4*>(s_x + rl * D + 4 * (lane + 32 * j)) = xv[j];
                 }
             }
-            float r_lo, r_hi, l_lo, l_hi;
-            const float norm = warp_estep_row<VEC4>(xv, s_mu, s_rinv, s_cst, K, D, lane, alpha, r_lo, r_hi, l_lo, l_hi);
-            if (lane < K) s_r[rl * K + lane] = r_lo;
-            if (lane + 32 < K) s_r[rl * K + lane + 32] = r_hi;
-            if (lane == 0) ll += norm;
+            if (packed) {
+                float ra, rb;
+                int kk;
+                const float norm = warp_estep_packed<VEC4>(xv, s_mu, s_rinv, s_cst, s_w, iso, K, D, lane, alpha, ra, rb, kk);
+                if ((lane & 3) == 0) {
+                    if (kk < K) s_r[rl * K + kk] = ra;
+                    if (kk + 8 < K) s_r[rl * K + kk + 8] = rb;
+                }
+                if (lane == 0) ll += norm;
+            } else {
+                float r_lo, r_hi, l_lo, l_hi;
+                const float norm = warp_estep_row<VEC4>(xv, s_mu, s_rinv, s_cst, K, D, lane, alpha, r_lo, r_hi, l_lo, l_hi);
+                if (lane < K) s_r[rl * K + lane] = r_lo;
+                if (lane + 32 < K) s_r[rl * K + lane + 32] = r_hi;
+                if (lane == 0) ll += norm;
+            }
         }
         __syncthreads();
         // phase 2: rank-nr update of the statistics, thread per output
@@ -536,7 +663,7 @@ extern "C" int mgp_em_stats(const float* bank, const int32_t* order, const float
     if (K > 64 || (D % 4) != 0 || D > 512) return MGP_ERR_UNSUPPORTED;
     const size_t stride = mgp_em_stat_stride(K, D, with_s2);
     const int nout = (K * D + 255) / 256;
-    const size_t smem = ((size_t)2 * K * D + (size_t)RB * D + (size_t)RB * K + K) * sizeof(float);
+    const size_t smem = ((size_t)2 * K * D + (size_t)RB * D + (size_t)RB * K + 2 * K) * sizeof(float);
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
     dim3 grid(C, n_split);
     cudaStream_t st = (cudaStream_t)stream;

@@ -229,8 +229,9 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     float* lval = reinterpret_cast<float*>(lkey + LCAP);    // [LCAP]
     unsigned* skey = reinterpret_cast<unsigned*>(lval + LCAP);                // [LCAP] sorted by row
     float* sval = reinterpret_cast<float*>(skey + LCAP);    // [LCAP]
-    int* bins = reinterpret_cast<int*>(sval + LCAP);        // [HW + 1] row histogram / start offsets
-    float* Qs = reinterpret_cast<float*>(bins + HW + 1);    // [C]  sum_t gl/exp(logit)      (wrong-class fold)
+    int* bins = reinterpret_cast<int*>(sval + LCAP);        // [8][HW] per-warp row histograms / start offsets
+    float* g2 = reinterpret_cast<float*>(bins + 8 * HW);    // [HW] sum_e a_e * w_p per row (isotropic sigma)
+    float* Qs = g2 + HW;                                    // [C]  sum_t gl/exp(logit)      (wrong-class fold)
     float* qg = Qs + C;                                     // [T]  gl/exp(logit) of the GT class
     __shared__ int wcount[8];
     __shared__ int lcount;
@@ -244,6 +245,7 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     const long long g = has_gt ? (long long)gt[b] : -1;
 
     for (int i = threadIdx.x; i < HW * pitch; i += 256) G[i] = 0.f;
+    for (int i = threadIdx.x; i < HW; i += 256) g2[i] = 0.f;
     if (has_gt) {
         for (int c = threadIdx.x; c < C; c += 256) {
             const size_t lo = ((size_t)b * C + c) * T;
@@ -320,47 +322,60 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
             // step so their L2 loads overlap.  Contributions to the lane's current row are summed in a
             // register and written to G only when the row changes (mined patches cluster on few rows);
             // the write-back is serialised over the 4 slots because slots may hold the same row.
-            // Stable counting sort of the entries by patch row (one warp, MATCH.ANY ranks: deterministic).
-            // Mined patches cluster on a few dozen rows, so after the sort a lane meets long runs of one row.
-            for (int i = threadIdx.x; i <= HW; i += 256) bins[i] = 0;
+            // Stable counting sort of the entries by patch row (deterministic): warp w owns the w-th contiguous
+            // eighth of the list; per-warp row histograms (MATCH.ANY, leader adds) -> per-warp start offsets ->
+            // in-order scatter.  Mined patches cluster on a few dozen rows, so after the sort a lane meets long
+            // runs of one row.
+            int* whist = bins;                                  // [8][HW] per-warp histograms, then start offsets
+            for (int i = threadIdx.x; i < 8 * HW; i += 256) whist[i] = 0;
             __syncthreads();
+            const int seg = (cnt + 7) / 8, sb = min(cnt, warp * seg), se = min(cnt, sb + seg);
+            for (int i0 = sb; i0 < se; i0 += 32) {
+                const int i = i0 + lane;
+                const int n = (i < se) ? (int)(lkey[i] & 1023u) : (0x10000 + lane);
+                const unsigned m = __match_any_sync(0xffffffffu, n);
+                if (i < se && (m & ((1u << lane) - 1u)) == 0) whist[warp * HW + n] += __popc(m);
+                __syncwarp();
+            }
+            __syncthreads();
+            // start offset of (warp, row): rows ascending, warps ascending inside a row
             if (warp == 0) {
-                for (int i0 = 0; i0 < cnt; i0 += 32) {
-                    const int i = i0 + lane;
-                    const int n = (i < cnt) ? (int)(lkey[i] & 1023u) : (0x10000 + lane);
-                    const unsigned m = __match_any_sync(0xffffffffu, n);
-                    if (i < cnt && (m & ((1u << lane) - 1u)) == 0) bins[n + 1] += __popc(m);
-                    __syncwarp();
-                }
-                // exclusive prefix over rows (HW <= 1024)
                 int carry = 0;
-                for (int r0 = 0; r0 <= HW; r0 += 32) {
+                for (int r0 = 0; r0 < HW; r0 += 32) {
                     const int r = r0 + lane;
-                    int v = (r <= HW) ? bins[r] : 0;
-                    int x = v;
+                    int tot = 0;
+                    if (r < HW)
+                        for (int wv = 0; wv < 8; ++wv) tot += whist[wv * HW + r];
+                    int x = tot;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int y = __shfl_up_sync(0xffffffffu, x, o);
                         if (lane >= o) x += y;
                     }
-                    if (r <= HW) bins[r] = carry + x;          // inclusive sum of counts up to row r-1 (bins[0] = 0)
+                    int start = carry + x - tot;                // exclusive prefix
+                    if (r < HW)
+                        for (int wv = 0; wv < 8; ++wv) {
+                            const int c = whist[wv * HW + r];
+                            whist[wv * HW + r] = start;
+                            start += c;
+                        }
                     carry += __shfl_sync(0xffffffffu, x, 31);
-                    __syncwarp();
                 }
-                for (int i0 = 0; i0 < cnt; i0 += 32) {
-                    const int i = i0 + lane;
-                    const unsigned kk = (i < cnt) ? lkey[i] : 0u;
-                    const int n = (i < cnt) ? (int)(kk & 1023u) : (0x10000 + lane);
-                    const unsigned m = __match_any_sync(0xffffffffu, n);
-                    if (i < cnt) {
-                        const int pos = bins[n] + __popc(m & ((1u << lane) - 1u));
-                        skey[pos] = kk;
-                        sval[pos] = lval[i];
-                    }
-                    __syncwarp();
-                    if (i < cnt && (m & ((1u << lane) - 1u)) == 0) bins[n] += __popc(m);
-                    __syncwarp();
+            }
+            __syncthreads();
+            for (int i0 = sb; i0 < se; i0 += 32) {
+                const int i = i0 + lane;
+                const unsigned kk = (i < se) ? lkey[i] : 0u;
+                const int n = (i < se) ? (int)(kk & 1023u) : (0x10000 + lane);
+                const unsigned m = __match_any_sync(0xffffffffu, n);
+                if (i < se) {
+                    const int pos = whist[warp * HW + n] + __popc(m & ((1u << lane) - 1u));
+                    skey[pos] = kk;
+                    sval[pos] = lval[i];
                 }
+                __syncwarp();
+                if (i < se && (m & ((1u << lane) - 1u)) == 0) whist[warp * HW + n] += __popc(m);
+                __syncwarp();
             }
             __syncthreads();
             // G[n] += sum_e a_e * wm_p  -  xhat_n * sum_e a_e * w_p : both sums are kept in registers for the
@@ -391,10 +406,11 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                     const bool valid = nn[h] >= 0;
                     const bool flush = valid && cur_n >= 0 && nn[h] != cur_n;
                     if (__any_sync(0xffffffffu, flush)) {
-                        const float xv = (flush && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
+                        const float xv = (aniso && flush && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (jj == j && flush && dok) G[(size_t)cur_n * pitch + dd] += s1 - xv * s2;
+                            if (jj == j && flush && dok) G[(size_t)cur_n * pitch + dd] += aniso ? (s1 - xv * s2) : s1;
+                            if (!aniso && warp == 0 && (lane & 7) == 0 && jj == j && flush) g2[cur_n] += s2;
                             __syncwarp();
                         }
                     }
@@ -406,10 +422,11 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                 }
             }
             {
-                const float xv = (cur_n >= 0 && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
+                const float xv = (aniso && cur_n >= 0 && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (jj == j && cur_n >= 0 && dok) G[(size_t)cur_n * pitch + dd] += s1 - xv * s2;
+                    if (jj == j && cur_n >= 0 && dok) G[(size_t)cur_n * pitch + dd] += aniso ? (s1 - xv * s2) : s1;
+                    if (!aniso && warp == 0 && (lane & 7) == 0 && jj == j && cur_n >= 0) g2[cur_n] += s2;
                     __syncwarp();
                 }
             }
@@ -422,7 +439,9 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     for (int n = warp; n < HW; n += 8) {
         float* dst = g_xhat + ((size_t)b * HW + n) * D + d0;
         const float* gr = G + (size_t)n * pitch;
-        for (int d = lane; d < dc; d += 32) dst[d] = gr[d];
+        const float* xr = xhat + ((size_t)b * HW + n) * D + d0;
+        const float gn = aniso ? 0.f : g2[n];                   // isotropic: - xhat_n * sum_e a_e w_p applied here
+        for (int d = lane; d < dc; d += 32) dst[d] = (gn != 0.f) ? fmaf(-gn, xr[d], gr[d]) : gr[d];
     }
 }
 
@@ -568,7 +587,7 @@ extern "C" int mgp_head_bwd(const float* grad_logits, const float* logits, const
     proto_weight_kernel<<<(unsigned)((npd + 255) / 256), 256, 0, st>>>(mu, sigma, w, wm, wsc, noniso, npd, D);
     MGP_CHECK_LAUNCH();
     const int DC = 64;                                       // D-chunk per CTA: 8 warps x 8 dims
-    size_t smem = (size_t)HW * (DC + 1) * 4 + (size_t)LCAP * 16 + (size_t)(HW + 1 + C + T) * 4;
+    size_t smem = (size_t)HW * (DC + 1) * 4 + (size_t)LCAP * 16 + (size_t)(9 * HW + C + T) * 4;
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
     MGP_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(B, (D + DC - 1) / DC);

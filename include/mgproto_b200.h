@@ -40,6 +40,10 @@ extern "C" {
 #define MGP_MATH_TC_REUSE 3 /* TC, operands (fp16 hi/lo split of x and of the prototypes) are
                                already staged in `ws` by the previous MGP_MATH_TC call with the
                                same shapes and pointers: only the GEMM kernel is launched       */
+#define MGP_MATH_TC_ISO 4   /* TC; the caller asserts that sigma is constant over d inside every
+                               prototype (true for every state the reference's loop reaches).
+                               Extends the tensor-core path to D = 256; the kernel traps if the
+                               assertion is false                                               */
 
 /* output layouts of mgp_logprob_fwd */
 #define MGP_OUT_LOGP_NP 0      /* out[n*P + p]           = log p      (ref: compute_log_prob)   */

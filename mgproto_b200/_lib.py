@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmgproto_b200.so")
 
-MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_AUTO, MGP_MATH_TC_REUSE = 0, 1, 2, 3
+MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_AUTO, MGP_MATH_TC_REUSE, MGP_MATH_TC_ISO = 0, 1, 2, 3, 4
 MGP_OUT_LOGP_NP, MGP_OUT_LOGP_BPHW, MGP_OUT_NEGP_BPHW = 0, 1, 2
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t

@@ -4,11 +4,11 @@
 int mgp_logprob_simt_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log,
                             float* out, int layout, int B, int HW, int P, int D, float* ws, cudaStream_t st);
 // logprob_tc.cu
-bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D);
+bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D, int assume_iso);
 size_t mgp_logprob_tc_ws_bytes(long long N, int P, int D);
 int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log,
                           float* out, int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes,
-                          int reuse_operands, cudaStream_t st);
+                          int reuse_operands, int assume_iso, cudaStream_t st);
 
 extern "C" int mgp_abi_version(void) { return MGP_ABI_VERSION; }
 
@@ -35,7 +35,7 @@ extern "C" int mgp_has_tensor_core_path(void) {
 extern "C" size_t mgp_logprob_ws_bytes(int B, int HW, int P, int D, int math) {
     size_t simt = ((size_t)P * D + P) * sizeof(float);
 #ifdef MGP_WITH_TC
-    if (math != MGP_MATH_FP32 && mgp_logprob_tc_supported(0, B, HW, P, D)) {
+    if (math != MGP_MATH_FP32 && mgp_logprob_tc_supported(0, B, HW, P, D, math == MGP_MATH_TC_ISO)) {
         size_t tc = mgp_logprob_tc_ws_bytes((long long)B * HW, P, D);
         return tc > simt ? tc : simt;
     }
@@ -57,14 +57,14 @@ extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const floa
     if (ws_bytes < mgp_logprob_ws_bytes(B, HW, P, D, math)) return MGP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
 #ifdef MGP_WITH_TC
-    if (math == MGP_MATH_TC || math == MGP_MATH_AUTO || math == MGP_MATH_TC_REUSE) {
-        if (mgp_logprob_tc_supported(out_layout, B, HW, P, D))
+    if (math == MGP_MATH_TC || math == MGP_MATH_AUTO || math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO) {
+        if (mgp_logprob_tc_supported(out_layout, B, HW, P, D, math == MGP_MATH_TC_ISO))
             return mgp_logprob_tc_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D, ws, ws_bytes,
-                                         math == MGP_MATH_TC_REUSE, st);
+                                         math == MGP_MATH_TC_REUSE, math == MGP_MATH_TC_ISO, st);
         if (math != MGP_MATH_AUTO) return MGP_ERR_UNSUPPORTED;
     }
 #else
-    if (math == MGP_MATH_TC || math == MGP_MATH_TC_REUSE) return MGP_ERR_UNSUPPORTED;
+    if (math == MGP_MATH_TC || math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO) return MGP_ERR_UNSUPPORTED;
 #endif
     return mgp_logprob_simt_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D,
                                    reinterpret_cast<float*>(ws), st);

@@ -359,6 +359,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     uint8_t* base_ptr = smem_raw + (base - raw);
 
     const bool gen = (*prm.noniso != 0);
+    if (gen && prm.D > 128) __trap();                             // MGP_MATH_TC_ISO promised isotropic sigma: fail loudly
     const int nkb = (gen ? 2 * prm.D : prm.D) / KB;               // K blocks per tile
     const int kcol0 = gen ? 0 : prm.D;                            // isotropic: only the [x] / [-2 w mu] half
     // [B,P,HW] through TMA: one x tile = one image (nti = round_up(HW,32) columns, UMMA N = nti) so that no
@@ -658,9 +659,11 @@ WsLayout ws_layout(long long N, int P, int D) {
 
 }  // namespace
 
-bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D) {
+bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D, int assume_iso) {
     (void)layout;
-    if (D != 64 && D != 128) return false;                  // K blocks of 64; x tile resident (general: 2D wide)
+    // K blocks of 64; the x tile (128 patches x K x 4 B, K = 2D when some sigma is anisotropic) must fit in
+    // shared memory: D <= 128 always, D = 256 only when the caller asserts isotropic sigma (MGP_MATH_TC_ISO)
+    if (!(D == 64 || D == 128 || (D == 256 && assume_iso))) return false;
     if ((long long)B * HW < 1 || P < 1) return false;
     return get_encode() != nullptr;
 }
@@ -669,7 +672,7 @@ size_t mgp_logprob_tc_ws_bytes(long long N, int P, int D) { return ws_layout(N, 
 
 int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log, float* out,
                           int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes, int reuse_operands,
-                          cudaStream_t st) {
+                          int assume_iso, cudaStream_t st) {
     const long long N = (long long)B * HW;
     const WsLayout w = ws_layout(N, P, D);
     if (ws_bytes < w.total) return MGP_ERR_WORKSPACE;
@@ -698,7 +701,7 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     const bool tma_ok = !(no_tma && atoi(no_tma));
     const bool tma_np = (layout == MGP_OUT_LOGP_NP) && (P % 4 == 0) && tma_ok;
     // [B,P,HW] through the 3-D map uses image-aligned x tiles (a chunk may not cross an image end)
-    const bool tma_bphw = (layout != MGP_OUT_LOGP_NP) && (HW % 4 == 0) && HW >= 32 && HW <= 256 && tma_ok;
+    const bool tma_bphw = (layout != MGP_OUT_LOGP_NP) && (HW % 4 == 0) && HW >= 32 && HW <= 256 && tma_ok && D <= 128;
     const bool tma_store = tma_np || tma_bphw;
     const uint32_t xbox = tma_bphw ? 32u : 128u;
     if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, xbox) || !make_map(&mxl, al, (uint64_t)N, 2 * D, xbox) ||
@@ -741,7 +744,7 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     prm.team = team;
     const int grid = n_teams * team;
     // shared memory: 1 KiB alignment slack + x tile(s) + prototype stages [+ 32 KiB TMA-store staging] + 2 KiB misc
-    const size_t x_max = (size_t)1024 * D;                        // general: 128 x 2D x 4 B (the isotropic tile is half)
+    const size_t x_max = (size_t)(assume_iso && D > 128 ? 512 : 1024) * D;   // general: 128 x 2D x 4 B (isotropic: half)
     if (1024 + x_max + (size_t)2 * 2 * SUB_BYTES + (tma_store ? STAGING_BYTES : 0) + 2048 > (size_t)227 * 1024)
         return MGP_ERR_UNSUPPORTED;
     const size_t smem = (size_t)227 * 1024;

@@ -9,14 +9,29 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_REUSE, MGP_OUT_LOGP_BPHW,
+from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, MGP_MATH_TC_REUSE, MGP_OUT_LOGP_BPHW,
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, check)
 
 __all__ = ["normalize_fwd", "logprob", "head_select", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
            "bank_linearize", "em_plan", "em_stats", "em_update", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
-MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE}
+MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE,
+              "tc_iso": MGP_MATH_TC_ISO}
+
+_iso_cache = {}
+
+
+def sigma_is_isotropic(sigma: torch.Tensor) -> bool:
+    """True if sigma is constant over the feature dim inside every prototype.  One tiny device reduction + host
+    read, cached per (storage, version): sigma never changes in the reference's training loop."""
+    key = (sigma.data_ptr(), sigma._version, tuple(sigma.shape))
+    hit = _iso_cache.get(key)
+    if hit is None:
+        hit = bool((sigma == sigma[..., :1]).all().item())
+        _iso_cache.clear()
+        _iso_cache[key] = hit
+    return hit
 
 _launches = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -94,6 +109,9 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
         raise RuntimeError("mgproto_b200: out has the wrong shape")
     lib = _lib.load()
     m = _math(math)
+    if m == MGP_MATH_AUTO and D > 128:
+        # wider features only fit the tensor-core tiles when sigma is isotropic: decided on the host (cached)
+        m = MGP_MATH_TC_ISO if (D == 256 and sigma_is_isotropic(sg)) else MGP_MATH_FP32
     nbytes = lib.mgp_logprob_ws_bytes(B_, HW_, P, D, m)
     if ws is None:
         ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)

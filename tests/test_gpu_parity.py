@@ -445,3 +445,38 @@ def test_logprob_tc_bphw_tma_path():
         a = ops.logprob(x, mu, sg, layout, B=B, HW=HW, math="tc")
         b = ops.logprob(x, mu, sg, layout, B=B, HW=HW, math="fp32")
         torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 if layout == 1 else 1e-12)
+
+
+def test_push_prototypes_matches_oracle():
+    """Prototype projection (push.py:82-200, numeric half) on a synthetic push set: chosen (image, patch) per
+    prototype and the copied feature vectors against the oracle run on the distance maps of push_forward."""
+    import mgproto_b200 as M
+    from oracle import mgproto_oracle as O
+    C, K, D, H, W, n = 5, 3, 64, 6, 6, 23
+    torch.manual_seed(4)
+    net = M.MGProto(features=nn.Sequential(nn.Conv2d(3, 16, 1)), img_size=H, prototype_shape=(C * K, D, 1, 1),
+                    proto_layer_rf_info=None, num_classes=C, add_on_layers_type="regular", sz_embedding=8,
+                    mem_capacity=8, mine_K=4).to(_dev())
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.randn(n, 3, H, W, generator=g)
+    labs = torch.randint(0, C, (n,), generator=g)
+    labs[:C] = torch.arange(C)
+    loader = [(imgs[i:i + 6], labs[i:i + 6]) for i in range(0, n, 6)]
+    with torch.no_grad():
+        feat, dist = net.push_forward(imgs.to(_dev()))
+    dist = dist.cpu().numpy()
+    feat = feat.cpu().numpy()
+    oi, ov = O.push_argmin(dist, labs.numpy(), K)
+    want = O.push_assign(ov, labs.numpy(), C, K)
+    mu0 = net.prototype_means.detach().clone()
+    res = M.push_prototypes(loader, net, log=lambda *_: None)
+    np.testing.assert_array_equal(res["image"], want)
+    for j in range(C * K):
+        c, k = divmod(j, K)
+        i = want[j]
+        if i < 0:
+            assert torch.equal(net.prototype_means[c, k], mu0[c, k])
+            continue
+        assert res["patch"][j] == oi[i, k]
+        hh, ww = divmod(int(oi[i, k]), W)
+        np.testing.assert_allclose(net.prototype_means[c, k].detach().cpu().numpy(), feat[i, :, hh, ww], rtol=1e-6)

@@ -63,36 +63,25 @@ __device__ __forceinline__ void warp_topT(const float* const (&rows)[NR], int rs
 // are disambiguated by their rank among earlier identical picks (MATCH.ANY).
 template <int R, int NR>
 __device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR], int rs, int HW, int T, int lane,
-                                                 float (&out_v)[NR], int (&out_i)[NR], unsigned* __restrict__ wsm) {
-    // per-warp scratch: the lanes' sorted lists and their unsorted originals, [row][slot][lane] (conflict-free);
-    // registers keep only the head of each list, a pop is one predicated LDS
-    unsigned* srt = wsm;
-    unsigned* org = wsm + NR * R * 32;
-    unsigned head[NR];
-    int ptr[NR];
+                                                 float (&out_v)[NR], int (&out_i)[NR]) {
+    unsigned orig[NR][R], key[NR][R];
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-        unsigned key[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int j = lane + 32 * r;
-            key[r] = (j < HW) ? f2key(rows[i][(size_t)j * rs]) : 0u;    // 0 sorts below every real float
-            org[(i * R + r) * 32 + lane] = key[r];
+            orig[i][r] = (j < HW) ? f2key(rows[i][(size_t)j * rs]) : 0u;
+            key[i][r] = orig[i][r];
         }
 #pragma unroll
         for (int a = 1; a < R; ++a)
 #pragma unroll
             for (int b = a; b >= 1; --b) {
-                const unsigned hi = max(key[b - 1], key[b]), lo = min(key[b - 1], key[b]);
-                key[b - 1] = hi;
-                key[b] = lo;
+                const unsigned hi = max(key[i][b - 1], key[i][b]), lo = min(key[i][b - 1], key[i][b]);
+                key[i][b - 1] = hi;
+                key[i][b] = lo;
             }
-#pragma unroll
-        for (int r = 0; r < R; ++r) srt[(i * R + r) * 32 + lane] = key[r];
-        head[i] = key[0];
-        ptr[i] = 0;
     }
-    __syncwarp();
     unsigned my_key[NR];
     int my_owner[NR];
 #pragma unroll
@@ -100,12 +89,13 @@ __device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR],
     for (int t = 0; t < T; ++t) {
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            const unsigned best = __reduce_max_sync(0xffffffffu, head[i]);
-            const unsigned m = __ballot_sync(0xffffffffu, head[i] == best);
+            const unsigned best = __reduce_max_sync(0xffffffffu, key[i][0]);
+            const unsigned m = __ballot_sync(0xffffffffu, key[i][0] == best);
             const int owner = __ffs(m) - 1;
             if (lane == owner) {
-                ++ptr[i];
-                head[i] = (ptr[i] < R) ? srt[(i * R + ptr[i]) * 32 + lane] : 0u;
+#pragma unroll
+                for (int r = 0; r + 1 < R; ++r) key[i][r] = key[i][r + 1];
+                key[i][R - 1] = 0u;
             }
             if (lane == t) { my_key[i] = best; my_owner[i] = owner; }
         }
@@ -119,7 +109,7 @@ __device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR],
         int rr = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const unsigned o = org[(i * R + r) * 32 + my_owner[i]];
+            const unsigned o = __shfl_sync(0xffffffffu, orig[i][r], my_owner[i]);
             const bool hit = (o == my_key[i]);
             if (hit && skip == 0) rr = r;
             if (hit) --skip;
@@ -127,7 +117,6 @@ __device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR],
         out_v[i] = key2f(my_key[i]);
         out_i[i] = my_owner[i] + 32 * rr;
     }
-    __syncwarp();
 }
 
 // FROM_NP = false: logp is [B,P,HW] (one contiguous row per (image, prototype)).
@@ -147,8 +136,7 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npl = nc * K;
     const int pitch = CT * K + 1;
-    unsigned* wsm = reinterpret_cast<unsigned*>(win + CT * K * T) + warp * (NR * (R <= 8 ? R : 1) * 64);
-    float* tile = win + CT * K * T + ((R <= 8) ? 8 * NR * R * 64 : 0);
+    float* tile = win + CT * K * T;
     if (FROM_NP) {
         const float* src = logp + (size_t)b * HW * P + (size_t)c0 * K;
         // asynchronous 4-byte copies (LDGSTS): every element of the block is in flight at once, no register
@@ -172,7 +160,7 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
         const int rs = FROM_NP ? pitch : 1;
         float v[NR];
         int ix[NR];
-        if (R <= 8) warp_topT_sorted<(R <= 8 ? R : 1), NR>(rows, rs, HW, T, lane, v, ix, wsm);
+        if (R <= 8) warp_topT_sorted<(R <= 8 ? R : 1), NR>(rows, rs, HW, T, lane, v, ix);
         else warp_topT<R, NR>(rows, rs, HW, T, lane, v, ix);
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
@@ -531,14 +519,14 @@ static int head_select_launch(const float* logp, int from_np, const float* weigh
     int CT = 64 / K;
     if (CT < 1) CT = 1;
     if (CT > C) CT = C;
-    const size_t smem0 = (size_t)CT * K * T * sizeof(float) + (from_np ? (size_t)HW * (CT * K + 1) * sizeof(float) : 0);
-    if (smem0 > 160 * 1024) return MGP_ERR_UNSUPPORTED;
+    size_t smem = (size_t)CT * K * T * sizeof(float);
+    if (from_np) smem += (size_t)HW * (CT * K + 1) * sizeof(float);
+    if (smem > 200 * 1024) return MGP_ERR_UNSUPPORTED;
     dim3 grid((C + CT - 1) / CT, B);
     cudaStream_t st = (cudaStream_t)stream;
     const int R = (HW + 31) / 32;
 #define MGP_LAUNCH_SEL2(RR, NRR, NP)                                                                                 \
     do {                                                                                                             \
-        const size_t smem = smem0 + ((RR) <= 8 ? (size_t)8 * (NRR) * (RR) * 64 * sizeof(unsigned) : 0);              \
         MGP_CUDA(cudaFuncSetAttribute(head_select_kernel<RR, NRR, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)smem));                                                                   \
         MGP_CUDA(cudaFuncSetAttribute(head_select_kernel<RR, NRR, NP>,                                               \

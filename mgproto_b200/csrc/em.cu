@@ -381,6 +381,244 @@ em_stats_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
 }
 
 // ---------------------------------------------------------------------------------------------
+// Specialised statistics kernel for the shipped shapes (K <= 16, D = 64 / 128 at compile time):
+// the generic kernel above spends most of its issue slots on index arithmetic and predicates (ncu: FFMA
+// is 18 % of its instructions).  Here a batch of up to `rbf` bank rows is staged once in shared memory
+// (cp.async, row pitch D+4 so both access patterns below are conflict-free) and
+//   phase 1 (E-step):   thread = (row, half of the components): one LDS.128 of x feeds KH*4 FMAs against
+//                       LDS.128 broadcasts of the packed means; the two halves meet with one shuffle pair
+//                       for the soft-max; no warp reductions over d.
+//   phase 2 (S1 [,S2]): thread = (dim d, row group): x[row][d] (1 LDS) times the row's K responsibilities
+//                       (RS/4 broadcast LDS.128) -> 2*KH FMAs, accumulators in registers.
+// Same outputs and layout as em_stats_kernel; grid (C, n_split).
+template <int D, int KH, bool WITH_S2>
+__global__ void __launch_bounds__(256, 3)
+em_stats_fast_kernel(const float* __restrict__ bank, const int32_t* __restrict__ order, const float* __restrict__ mu,
+                     const float* __restrict__ sigma, const float* __restrict__ weight, float alpha, int row_begin,
+                     int row_end, int n_split, int rbf, float* __restrict__ stats, size_t stat_stride, int C, int K,
+                     int cap) {
+    constexpr int DP = D + 4, K2 = 2 * KH, RS = (K2 + 3) & ~3, G = 256 / D, D4 = D / 4;
+    const int c = blockIdx.x;
+    if (order[c] < 0) return;
+    extern __shared__ __align__(16) float sm[];
+    const int xfl = max(rbf * DP, G * K2 * D);
+    float* s_a = sm;                     // [K2][DP]  iso: -2 w_k mu_k, else mu_k   (rows >= K are zero)
+    float* s_ri = s_a + K2 * DP;         // [K2][DP]  1/(sigma+eps)
+    float* s_x = s_ri + K2 * DP;         // [rbf][DP] bank rows of the batch (reused for the group combine)
+    float* s_r = s_x + xfl;              // [rbf][RS] smoothed responsibilities
+    float* s_cst = s_r + rbf * RS;       // [K2]
+    float* s_w = s_cst + K2;             // [K2]
+    float* s_red = s_w + K2;             // [8][K2]
+    __shared__ float s_ll[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = C * K;
+    const int split = blockIdx.y;
+    const int rows = row_end - row_begin;
+    const int per = (rows + n_split - 1) / n_split;
+    const int seg_b = row_begin + split * per;
+    const int seg_e = min(row_end, seg_b + per);
+    const float* sg_c = sigma + (size_t)c * K * D;
+    const float* mu_c = mu + (size_t)c * K * D;
+
+    bool same = true;
+    for (int i = tid; i < K * D; i += 256) same = same && (sg_c[i] == sg_c[(i / D) * D]);
+    const bool iso = __syncthreads_and(same ? 1 : 0) != 0;
+    for (int i = tid; i < K2 * D; i += 256) {
+        const int k = i / D, d = i - k * D;
+        float av = 0.f, rv = 0.f;
+        if (k < K) {
+            rv = 1.0f / (sg_c[i] + EM_EPS);                                           // ref :333
+            av = iso ? -2.0f * rv * rv * mu_c[i] : mu_c[i];
+        }
+        s_a[k * DP + d] = av;
+        s_ri[k * DP + d] = rv;
+    }
+    for (int k = warp; k < K2; k += 8) {
+        float ls = 0.f, mm = 0.f;
+        if (k < K)
+            for (int d = lane; d < D; d += 32) {
+                ls += logf(sg_c[k * D + d] + EM_EPS);                                 // ref :334
+                const float m = mu_c[k * D + d];
+                mm = fmaf(m, m, mm);
+            }
+        ls = warp_sum(ls);
+        mm = warp_sum(mm);
+        if (lane == 0) {
+            float wk = 0.f, cst = 0.f;
+            if (k < K) {
+                const float rinv0 = 1.0f / (sg_c[k * D] + EM_EPS);
+                wk = rinv0 * rinv0;
+                cst = -0.5f * (float)D * MGP_LOG_2PI - ls + logf(weight[(size_t)c * P + c * K + k] + EM_EPS) -
+                      (iso ? 0.5f * wk * mm : 0.f);
+            }
+            s_w[k] = wk;
+            s_cst[k] = cst;
+        }
+    }
+    __syncthreads();
+
+    float a1[K2], a2[WITH_S2 ? K2 : 1], s0[KH];
+#pragma unroll
+    for (int i = 0; i < K2; ++i) a1[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < (WITH_S2 ? K2 : 1); ++i) a2[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) s0[i] = 0.f;
+    float ll = 0.f;
+    const int row = tid >> 1, half = tid & 1;
+    const int pd = tid & (D - 1), pg = tid / D;
+    const float inv_den = 1.0f / (1.0f + (float)K * alpha);
+    const unsigned sx_addr = (unsigned)__cvta_generic_to_shared(s_x);
+
+    for (int r0 = seg_b; r0 < seg_e; r0 += rbf) {
+        const int nr = min(rbf, seg_e - r0);
+        const float* src = bank + ((size_t)c * cap + r0) * D;
+        for (int q = tid; q < nr * D4; q += 256) {
+            const int rr = q / D4, c4 = q - rr * D4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx_addr + (unsigned)(rr * DP + 4 * c4) * 4u),
+                         "l"(src + (size_t)q * 4)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // phase 1
+        if (warp * 16 < nr) {
+            const float* xr = s_x + min(row, nr - 1) * DP;
+            const float* ar = s_a + half * KH * DP;
+            const float* rr_ = s_ri + half * KH * DP;
+            float acc[KH], xx = 0.f;
+#pragma unroll
+            for (int i = 0; i < KH; ++i) acc[i] = 0.f;
+            if (iso) {
+#pragma unroll 4
+                for (int j = 0; j < D4; ++j) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
+                    xx = fmaf(xv.x, xv.x, xx); xx = fmaf(xv.y, xv.y, xx);
+                    xx = fmaf(xv.z, xv.z, xx); xx = fmaf(xv.w, xv.w, xx);
+#pragma unroll
+                    for (int i = 0; i < KH; ++i) {
+                        const float4 m = *reinterpret_cast<const float4*>(ar + i * DP + 4 * j);
+                        acc[i] = fmaf(xv.x, m.x, acc[i]); acc[i] = fmaf(xv.y, m.y, acc[i]);
+                        acc[i] = fmaf(xv.z, m.z, acc[i]); acc[i] = fmaf(xv.w, m.w, acc[i]);
+                    }
+                }
+            } else {
+#pragma unroll 2
+                for (int j = 0; j < D4; ++j) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
+#pragma unroll
+                    for (int i = 0; i < KH; ++i) {
+                        const float4 m = *reinterpret_cast<const float4*>(ar + i * DP + 4 * j);
+                        const float4 ri = *reinterpret_cast<const float4*>(rr_ + i * DP + 4 * j);
+                        float t;
+                        t = (xv.x - m.x) * ri.x; acc[i] = fmaf(t, t, acc[i]);
+                        t = (xv.y - m.y) * ri.y; acc[i] = fmaf(t, t, acc[i]);
+                        t = (xv.z - m.z) * ri.z; acc[i] = fmaf(t, t, acc[i]);
+                        t = (xv.w - m.w) * ri.w; acc[i] = fmaf(t, t, acc[i]);
+                    }
+                }
+            }
+            float wl[KH], mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < KH; ++i) {
+                const int k = half * KH + i;
+                const float q = iso ? fmaf(s_w[k], xx, acc[i]) : acc[i];
+                wl[i] = (k < K) ? s_cst[k] - 0.5f * q : -INFINITY;                    // lp + log(pi + eps)  (ref :316)
+                mx = fmaxf(mx, wl[i]);
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            float se = 0.f;
+#pragma unroll
+            for (int i = 0; i < KH; ++i) {
+                wl[i] = (half * KH + i < K) ? expf(wl[i] - mx) : 0.f;
+                se += wl[i];
+            }
+            se += __shfl_xor_sync(0xffffffffu, se, 1);
+            const float inv_se = 1.0f / se;
+            const bool live = row < nr;
+#pragma unroll
+            for (int i = 0; i < KH; ++i) {
+                const int k = half * KH + i;
+                const float r = (k < K && live) ? fmaf(wl[i], inv_se, alpha) * inv_den : 0.f;   // ref :380-383
+                s0[i] += r;
+                if (live) s_r[row * RS + k] = r;
+            }
+            if (live && half == 0) ll += mx + logf(se);                               // logsumexp (ref :318)
+        }
+        __syncthreads();
+        // phase 2
+        {
+            const int per_g = (nr + G - 1) / G;
+            const int rb = pg * per_g, re = min(nr, rb + per_g);
+#pragma unroll 2
+            for (int rl = rb; rl < re; ++rl) {
+                const float xv = s_x[rl * DP + pd];
+                float rv[RS];
+#pragma unroll
+                for (int i = 0; i < RS / 4; ++i)
+                    *reinterpret_cast<float4*>(rv + 4 * i) = *reinterpret_cast<const float4*>(s_r + rl * RS + 4 * i);
+#pragma unroll
+                for (int i = 0; i < K2; ++i) {
+                    a1[i] = fmaf(rv[i], xv, a1[i]);
+                    if (WITH_S2) a2[i] = fmaf(rv[i] * xv, xv, a2[i]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    float* out = stats + ((size_t)c * n_split + split) * stat_stride;
+    // S0 and the score: lanes of equal half hold partial sums
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+#pragma unroll
+        for (int o = 2; o < 32; o <<= 1) s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
+        if (lane < 2) s_red[warp * K2 + lane * KH + i] = s0[i];
+    }
+    ll = warp_sum(ll);
+    if (lane == 0) s_ll[warp] = ll;
+    // combine the G row groups of S1 (and S2) through shared memory in a fixed order
+#pragma unroll
+    for (int i = 0; i < K2; ++i) s_x[(pg * K2 + i) * D + pd] = a1[i];
+    __syncthreads();
+    if (tid < K) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w * K2 + tid];
+        out[tid] = t;
+    }
+    if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_ll[w];
+        out[stat_stride - 1] = t;
+    }
+    const int KD = K * D;
+    for (int o = tid; o < KD; o += 256) {
+        const int k = o / D, d = o - k * D;
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) t += s_x[(g * K2 + k) * D + d];
+        out[K + o] = t;
+    }
+    if (WITH_S2) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < K2; ++i) s_x[(pg * K2 + i) * D + pd] = a2[i];
+        __syncthreads();
+        for (int o = tid; o < KD; o += 256) {
+            const int k = o / D, d = o - k * D;
+            float t = 0.f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) t += s_x[(g * K2 + k) * D + d];
+            out[K + KD + o] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct AdamCfg {
     float lr, beta1, beta2, eps;
 };
@@ -662,6 +900,34 @@ extern "C" int mgp_em_stats(const float* bank, const int32_t* order, const float
         return MGP_ERR_INVALID;
     if (K > 64 || (D % 4) != 0 || D > 512) return MGP_ERR_UNSUPPORTED;
     const size_t stride = mgp_em_stat_stride(K, D, with_s2);
+    static const bool legacy = (getenv("MGP_EM_LEGACY") != nullptr);
+    if (!legacy && K <= 16 && (D == 64 || D == 128)) {
+        const int kh = (K + 1) / 2 <= 3 ? 3 : ((K + 1) / 2 <= 5 ? 5 : 8);
+        const int per = (row_end - row_begin + n_split - 1) / n_split;
+        const int nb = (per + 127) / 128;
+        int rbf = (((per + nb - 1) / nb) + 3) & ~3;
+        if (rbf < 32) rbf = 32;
+        const int k2 = 2 * kh, rs = (k2 + 3) & ~3, g = 256 / D, dp = D + 4;
+        const int xfl = rbf * dp > g * k2 * D ? rbf * dp : g * k2 * D;
+        const size_t fsmem = ((size_t)2 * k2 * dp + xfl + (size_t)rbf * rs + 2 * k2 + 8 * k2) * sizeof(float);
+        dim3 fgrid(C, n_split);
+        cudaStream_t fst = (cudaStream_t)stream;
+#define MGP_EM_FAST(DD, KK, SS)                                                                                     \
+    if (D == DD && kh == KK && (with_s2 != 0) == SS) {                                                              \
+        MGP_CUDA(cudaFuncSetAttribute(em_stats_fast_kernel<DD, KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)fsmem));                                                                 \
+        em_stats_fast_kernel<DD, KK, SS><<<fgrid, 256, fsmem, fst>>>(bank, order, mu, sigma, weight_cp, alpha,       \
+                                                                     row_begin, row_end, n_split, rbf, stats,       \
+                                                                     stride, C, K, cap);                            \
+        MGP_CHECK_LAUNCH();                                                                                         \
+        return MGP_OK;                                                                                              \
+    }
+        MGP_EM_FAST(128, 3, false) MGP_EM_FAST(128, 5, false) MGP_EM_FAST(128, 8, false)
+        MGP_EM_FAST(64, 3, false) MGP_EM_FAST(64, 5, false) MGP_EM_FAST(64, 8, false)
+        MGP_EM_FAST(128, 3, true) MGP_EM_FAST(128, 5, true) MGP_EM_FAST(128, 8, true)
+        MGP_EM_FAST(64, 3, true) MGP_EM_FAST(64, 5, true) MGP_EM_FAST(64, 8, true)
+#undef MGP_EM_FAST
+    }
     const int nout = (K * D + 255) / 256;
     const size_t smem = ((size_t)2 * K * D + (size_t)RB * D + (size_t)RB * K + 2 * K) * sizeof(float);
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;

@@ -109,7 +109,7 @@ class MGProto(nn.Module):
 
         # B200 knobs (not in the reference)
         self.math_mode = "auto"          # 'fp32' exact SIMT | 'tc' tcgen05 fp16x3 | 'auto'
-        self.em_n_split = 8              # row splits of the EM statistics reduction
+        self.em_n_split = 2              # row splits of the EM statistics reduction
         self.em_group = None             # torch.distributed process group for the sharded EM (parallel.py)
         self._em_pending = None          # (pinned n_active, event) of the last update_GMM
 

@@ -210,11 +210,10 @@ __global__ void proto_weight_kernel(const float* __restrict__ mu, const float* _
 
 constexpr int LCAP = 2304;   // entries per drain (>= P + K(T-1) of the labelled cfg: one drain per image)
 
-// grid (B, D/DC), DC = 64.  Warp w owns the 8-dim column slice [8w, 8w+8) of every row of the image's
-// gradient tile G[HW][DC]: all warps walk the whole (compacted, fixed-order) entry list, four entries per
-// step (lane = 8*j + dim), so the work is balanced however the mined patches cluster, there are no
-// atomics and the summation order is fixed.  The prototype / patch row loads of the four entries are
-// issued together; the read-modify-write of G is serialised over j because entries often share a row.
+// grid (B, D/DC), DC = 64: CTA (b, j) builds dims [64j, 64j+64) of image b's gradient tile G[HW][DC] in shared
+// memory.  Entries with gradient are compacted in a fixed order, stably counting-sorted by patch row, then each
+// warp walks one eighth of the sorted list with lanes owning two dims each (see the walk below): balanced
+// however the mined patches cluster, no atomics, fixed summation order.
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, const float* __restrict__ vals,
                 const int32_t* __restrict__ idx, const float* __restrict__ weight, const int64_t* __restrict__ gt,
@@ -222,7 +221,7 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                 const float* __restrict__ wsc, const int* __restrict__ noniso, float* __restrict__ g_xhat, int HW,
                 int C, int K, int D, int T, int DC) {
     extern __shared__ float smem[];
-    const int pitch = DC + 1;
+    const int pitch = DC;                                   // even: rows are float2-addressable
     const bool aniso = (*noniso != 0);
     float* G = smem;                                        // [HW][pitch]
     unsigned* lkey = reinterpret_cast<unsigned*>(G + (size_t)HW * pitch);     // [LCAP] p*1024 + n
@@ -235,6 +234,9 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     float* qg = Qs + C;                                     // [T]  gl/exp(logit) of the GT class
     __shared__ int wcount[8];
     __shared__ int lcount;
+    __shared__ __align__(8) float part[16 * 64];            // boundary runs of the warps' list ranges
+    __shared__ float part2[16];
+    __shared__ int prow[16];
 
     const int b = blockIdx.x;
     const int d0 = blockIdx.y * DC;
@@ -266,8 +268,6 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     // gradient (wrong-class levels alias level 0, ref model.py:221); without labels all P*T entries
     const bool gvalid = has_gt && g >= 0 && g < C;
     const int E = has_gt ? (P + (gvalid ? K * (T - 1) : 0)) : P * T;
-    const int jj = lane >> 3, dd = warp * 8 + (lane & 7);   // entry slot / owned dim of this lane
-    const bool dok = dd < dc;
     for (int e0 = 0; e0 < E; e0 += 256) {
         const int e = e0 + threadIdx.x;
         float a = 0.f;
@@ -318,10 +318,6 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
         const int cnt = lcount;
         const bool last = (e0 + 256 >= E);
         if (cnt + 256 > LCAP || last) {
-            // Each lane (slot jj, dim dd) walks entries jj, jj+4, ...; 16 entries (4 per lane) are fetched per
-            // step so their L2 loads overlap.  Contributions to the lane's current row are summed in a
-            // register and written to G only when the row changes (mined patches cluster on few rows);
-            // the write-back is serialised over the 4 slots because slots may hold the same row.
             // Stable counting sort of the entries by patch row (deterministic): warp w owns the w-th contiguous
             // eighth of the list; per-warp row histograms (MATCH.ANY, leader adds) -> per-warp start offsets ->
             // in-order scatter.  Mined patches cluster on a few dozen rows, so after the sort a lane meets long
@@ -378,55 +374,107 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                 __syncwarp();
             }
             __syncthreads();
-            // G[n] += sum_e a_e * wm_p  -  xhat_n * sum_e a_e * w_p : both sums are kept in registers for the
-            // lane's current row; xhat is touched only at write-back, and w_p is a per-prototype scalar when
-            // every sigma is isotropic (one row load per entry instead of three)
-            int cur_n = -1;
-            float s1 = 0.f, s2 = 0.f;
-            const float* xcol = xhat + (size_t)b * HW * D + d0 + dd;
-            for (int i0 = 0; i0 < cnt; i0 += 16) {
-                float fw[4], fm[4], aa[4];
-                int nn[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const int i = i0 + 4 * h + jj;
-                    const bool ok = i < cnt;
-                    const unsigned kk = ok ? skey[i] : 0u;
-                    aa[h] = ok ? sval[i] : 0.f;
-                    const int p = kk >> 10;
-                    nn[h] = ok ? (int)(kk & 1023u) : -1;
-                    fw[h] = fm[h] = 0.f;
-                    if (ok && dok) {
-                        fm[h] = __ldg(wm + (size_t)p * D + d0 + dd);
-                        fw[h] = aniso ? __ldg(w + (size_t)p * D + d0 + dd) : __ldg(wsc + p);
+            // Walk: warp w owns the w-th eighth of the row-sorted list (balanced however the patches cluster),
+            // lanes own two dims each, so one instruction handles one entry x 64 dims and the prototype rows
+            // are read as coalesced 256-byte segments, eight in flight.  Per row:
+            //   G[n] += sum_e a_e * wm_p  -  xhat_n * sum_e a_e * w_p
+            // (w_p is a per-prototype scalar when every sigma is isotropic: then the second sum is the scalar
+            // g2[n], applied at copy-out).  Runs inside a warp's range are complete rows (single writer);
+            // the first and last run of a range may continue in the neighbour's range: they are parked in
+            // `part` and folded in by one warp in a fixed order -> no atomics, deterministic.
+            if (threadIdx.x < 16) prow[threadIdx.x] = -1;
+            __syncthreads();
+            {
+                const int wseg = (cnt + 7) / 8, wb = min(cnt, warp * wseg), we = min(cnt, wb + wseg);
+                const int dl = 2 * lane;
+                const bool dok2 = dl < dc;
+                const float* wmcol = wm + d0 + dl;
+                const float* wcol = w + d0 + dl;
+                const float* xcol2 = xhat + (size_t)b * HW * D + d0 + dl;
+                int cur_n = -1;
+                bool first_run = true;
+                float2 s1 = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
+                float s2 = 0.f;
+                auto flush = [&](int slot) {
+                    float2 v = s1;
+                    if (aniso && dok2) {
+                        const float2 xv = __ldg(reinterpret_cast<const float2*>(xcol2 + (size_t)cur_n * D));
+                        v.x = fmaf(-xv.x, s2v.x, v.x);
+                        v.y = fmaf(-xv.y, s2v.y, v.y);
                     }
-                }
+                    if (slot < 0) {
+                        if (dok2) {
+                            float2* gp = reinterpret_cast<float2*>(G + (size_t)cur_n * pitch + dl);
+                            float2 t = *gp;
+                            t.x += v.x;
+                            t.y += v.y;
+                            *gp = t;
+                        }
+                        if (lane == 0) g2[cur_n] += s2;
+                    } else {
+                        if (dok2) *reinterpret_cast<float2*>(part + (warp * 2 + slot) * 64 + dl) = v;
+                        if (lane == 0) { part2[warp * 2 + slot] = s2; prow[warp * 2 + slot] = cur_n; }
+                    }
+                };
+                for (int i0 = wb; i0 < we; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool ok = i < we;
+                    const unsigned kk = ok ? skey[i] : 0u;
+                    const float av = ok ? sval[i] : 0.f;
+                    const float v2 = (ok && !aniso) ? av * __ldg(wsc + (kk >> 10)) : 0.f;
+                    const int m = min(32, we - i0);
+                    for (int j0 = 0; j0 < m; j0 += 8) {
+                        float2 fm[8], fw[8];
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const bool valid = nn[h] >= 0;
-                    const bool flush = valid && cur_n >= 0 && nn[h] != cur_n;
-                    if (__any_sync(0xffffffffu, flush)) {
-                        const float xv = (aniso && flush && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
+                        for (int u = 0; u < 8; ++u) {
+                            const unsigned ku = __shfl_sync(0xffffffffu, kk, j0 + u);
+                            const size_t po = (size_t)(ku >> 10) * D;
+                            const bool v = (j0 + u < m) && dok2;
+                            fm[u] = v ? __ldg(reinterpret_cast<const float2*>(wmcol + po)) : make_float2(0.f, 0.f);
+                            fw[u] = (v && aniso) ? __ldg(reinterpret_cast<const float2*>(wcol + po)) : make_float2(0.f, 0.f);
+                        }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (jj == j && flush && dok) G[(size_t)cur_n * pitch + dd] += aniso ? (s1 - xv * s2) : s1;
-                            if (!aniso && warp == 0 && (lane & 7) == 0 && jj == j && flush) g2[cur_n] += s2;
-                            __syncwarp();
+                        for (int u = 0; u < 8; ++u) {
+                            const int n = (int)(__shfl_sync(0xffffffffu, kk, j0 + u) & 1023u);
+                            const float a = __shfl_sync(0xffffffffu, av, j0 + u);
+                            const float b2 = __shfl_sync(0xffffffffu, v2, j0 + u);
+                            if (j0 + u < m) {
+                                if (n != cur_n) {
+                                    if (cur_n >= 0) {
+                                        flush(first_run ? 0 : -1);
+                                        first_run = false;
+                                    }
+                                    cur_n = n;
+                                    s1 = make_float2(0.f, 0.f);
+                                    s2v = make_float2(0.f, 0.f);
+                                    s2 = 0.f;
+                                }
+                                s1.x = fmaf(a, fm[u].x, s1.x);
+                                s1.y = fmaf(a, fm[u].y, s1.y);
+                                s2v.x = fmaf(a, fw[u].x, s2v.x);
+                                s2v.y = fmaf(a, fw[u].y, s2v.y);
+                                s2 += b2;
+                            }
                         }
                     }
-                    if (valid) {
-                        if (nn[h] != cur_n) { cur_n = nn[h]; s1 = 0.f; s2 = 0.f; }
-                        s1 = fmaf(aa[h], fm[h], s1);
-                        s2 = fmaf(aa[h], fw[h], s2);
-                    }
                 }
+                if (cur_n >= 0) flush(first_run ? 0 : 1);
             }
-            {
-                const float xv = (aniso && cur_n >= 0 && dok) ? __ldg(xcol + (size_t)cur_n * D) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (jj == j && cur_n >= 0 && dok) G[(size_t)cur_n * pitch + dd] += aniso ? (s1 - xv * s2) : s1;
-                    if (!aniso && warp == 0 && (lane & 7) == 0 && jj == j && cur_n >= 0) g2[cur_n] += s2;
+            __syncthreads();
+            if (warp == 0) {
+                const int dl = 2 * lane;
+                for (int i = 0; i < 16; ++i) {
+                    const int n = prow[i];
+                    if (n < 0) continue;
+                    if (dl < dc) {
+                        float2* gp = reinterpret_cast<float2*>(G + (size_t)n * pitch + dl);
+                        const float2 v = *reinterpret_cast<const float2*>(part + i * 64 + dl);
+                        float2 t = *gp;
+                        t.x += v.x;
+                        t.y += v.y;
+                        *gp = t;
+                    }
+                    if (lane == 0) g2[n] += part2[i];
                     __syncwarp();
                 }
             }
@@ -587,7 +635,7 @@ extern "C" int mgp_head_bwd(const float* grad_logits, const float* logits, const
     proto_weight_kernel<<<(unsigned)((npd + 255) / 256), 256, 0, st>>>(mu, sigma, w, wm, wsc, noniso, npd, D);
     MGP_CHECK_LAUNCH();
     const int DC = 64;                                       // D-chunk per CTA: 8 warps x 8 dims
-    size_t smem = (size_t)HW * (DC + 1) * 4 + (size_t)LCAP * 16 + (size_t)(9 * HW + C + T) * 4;
+    size_t smem = (size_t)HW * DC * 4 + (size_t)LCAP * 16 + (size_t)(9 * HW + C + T) * 4;
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
     MGP_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(B, (D + DC - 1) / DC);

@@ -2,6 +2,7 @@
 // pi mix and log; its backward; and the push-projection argmin (f1).
 // ref: model.py:188-206, :214-222, :254, :54-74; push.py:125-158.
 #include "mgp_common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -214,7 +215,7 @@ constexpr int LCAP = 2304;   // entries per drain (>= P + K(T-1) of the labelled
 // memory.  Entries with gradient are compacted in a fixed order, stably counting-sorted by patch row, then each
 // warp walks one eighth of the sorted list with lanes owning two dims each (see the walk below): balanced
 // however the mined patches cluster, no atomics, fixed summation order.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, const float* __restrict__ vals,
                 const int32_t* __restrict__ idx, const float* __restrict__ weight, const int64_t* __restrict__ gt,
                 const float* __restrict__ xhat, const float* __restrict__ w, const float* __restrict__ wm,
@@ -249,17 +250,33 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     for (int i = threadIdx.x; i < HW * pitch; i += 256) G[i] = 0.f;
     for (int i = threadIdx.x; i < HW; i += 256) g2[i] = 0.f;
     if (has_gt) {
-        for (int c = threadIdx.x; c < C; c += 256) {
-            const size_t lo = ((size_t)b * C + c) * T;
-            float q = 0.f;
-            for (int t = 0; t < T; ++t) q += gl[lo + t] / expf(logits[lo + t]);
-            Qs[c] = q;
-        }
-        if (g >= 0 && g < C)
-            for (int t = threadIdx.x; t < T; t += 256) {
-                const size_t lo = ((size_t)b * C + (size_t)g) * T;
-                qg[t] = gl[lo + t] / expf(logits[lo + t]);
+        if (C * T <= 2 * LCAP) {
+            // q[c][t] = gl / exp(logit) for the whole image in one coalesced pass (staged in the sorted-list
+            // area, free until the first drain), then one thread per class sums its T levels
+            float* qtmp = reinterpret_cast<float*>(skey);
+            const size_t lo = (size_t)b * C * T;
+            for (int i = threadIdx.x; i < C * T; i += 256) qtmp[i] = gl[lo + i] / expf(logits[lo + i]);
+            __syncthreads();
+            for (int c = threadIdx.x; c < C; c += 256) {
+                float q = 0.f;
+                for (int t = 0; t < T; ++t) q += qtmp[c * T + t];
+                Qs[c] = q;
             }
+            if (g >= 0 && g < C)
+                for (int t = threadIdx.x; t < T; t += 256) qg[t] = qtmp[(int)g * T + t];
+        } else {
+            for (int c = threadIdx.x; c < C; c += 256) {
+                const size_t lo = ((size_t)b * C + c) * T;
+                float q = 0.f;
+                for (int t = 0; t < T; ++t) q += gl[lo + t] / expf(logits[lo + t]);
+                Qs[c] = q;
+            }
+            if (g >= 0 && g < C)
+                for (int t = threadIdx.x; t < T; t += 256) {
+                    const size_t lo = ((size_t)b * C + (size_t)g) * T;
+                    qg[t] = gl[lo + t] / expf(logits[lo + t]);
+                }
+        }
     }
     if (threadIdx.x == 0) lcount = 0;
     __syncthreads();
@@ -268,10 +285,11 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     // gradient (wrong-class levels alias level 0, ref model.py:221); without labels all P*T entries
     const bool gvalid = has_gt && g >= 0 && g < C;
     const int E = has_gt ? (P + (gvalid ? K * (T - 1) : 0)) : P * T;
-    for (int e0 = 0; e0 < E; e0 += 256) {
-        const int e = e0 + threadIdx.x;
-        float a = 0.f;
-        unsigned key = 0;
+    // entry e -> (coefficient a, key p*1024 + n); evaluated one iteration ahead so the gathers of the next
+    // 256 entries are in flight while the current ones are compacted
+    auto entry = [&](int e, float& a, unsigned& key) {
+        a = 0.f;
+        key = 0;
         if (e < E) {
             int p, t;
             float qv;
@@ -297,6 +315,14 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
             a = qv * __ldg(weight + (size_t)c * P + p) * vals[vi];
             key = (unsigned)p * 1024u + (unsigned)idx[vi];
         }
+    };
+    float a_nx;
+    unsigned key_nx;
+    entry(threadIdx.x, a_nx, key_nx);
+    for (int e0 = 0; e0 < E; e0 += 256) {
+        const float a = a_nx;
+        const unsigned key = key_nx;
+        entry(e0 + 256 + threadIdx.x, a_nx, key_nx);
         const bool keep = (a != 0.f);
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) wcount[warp] = __popc(bal);
@@ -416,29 +442,32 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                         if (lane == 0) { part2[warp * 2 + slot] = s2; prow[warp * 2 + slot] = cur_n; }
                     }
                 };
-                for (int i0 = wb; i0 < we; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool ok = i < we;
-                    const unsigned kk = ok ? skey[i] : 0u;
-                    const float av = ok ? sval[i] : 0.f;
-                    const float v2 = (ok && !aniso) ? av * __ldg(wsc + (kk >> 10)) : 0.f;
-                    const int m = min(32, we - i0);
-                    for (int j0 = 0; j0 < m; j0 += 8) {
-                        float2 fm[8], fw[8];
+                // lanes beyond dc read (and discard) the CTA's first dims; list slots beyond the range repeat the
+                // range's last entry with a zero coefficient -> unconditional loads, no per-entry predicates
+                const float* wmcol_l = dok2 ? wmcol : wm + d0;
+                const float* wcol_l = dok2 ? wcol : w + d0;
+                auto walk = [&](auto aniso_tag) {
+                    constexpr bool AN = decltype(aniso_tag)::value;
+                    for (int i0 = wb; i0 < we; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool ok = i < we;
+                        const unsigned kk = skey[ok ? i : we - 1];
+                        const float av = ok ? sval[i] : 0.f;
+                        const float v2 = (!AN && ok) ? av * __ldg(wsc + (kk >> 10)) : 0.f;
+                        const int m = min(32, we - i0);
+                        for (int j0 = 0; j0 < m; j0 += 8) {
+                            float2 fm[8], fw[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const unsigned ku = __shfl_sync(0xffffffffu, kk, j0 + u);
-                            const size_t po = (size_t)(ku >> 10) * D;
-                            const bool v = (j0 + u < m) && dok2;
-                            fm[u] = v ? __ldg(reinterpret_cast<const float2*>(wmcol + po)) : make_float2(0.f, 0.f);
-                            fw[u] = (v && aniso) ? __ldg(reinterpret_cast<const float2*>(wcol + po)) : make_float2(0.f, 0.f);
-                        }
+                            for (int u = 0; u < 8; ++u) {
+                                const unsigned ku = __shfl_sync(0xffffffffu, kk, j0 + u);
+                                const unsigned po = (ku >> 10) * (unsigned)D;
+                                fm[u] = __ldg(reinterpret_cast<const float2*>(wmcol_l + po));
+                                if (AN) fw[u] = __ldg(reinterpret_cast<const float2*>(wcol_l + po));
+                            }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int n = (int)(__shfl_sync(0xffffffffu, kk, j0 + u) & 1023u);
-                            const float a = __shfl_sync(0xffffffffu, av, j0 + u);
-                            const float b2 = __shfl_sync(0xffffffffu, v2, j0 + u);
-                            if (j0 + u < m) {
+                            for (int u = 0; u < 8; ++u) {
+                                const int n = (int)(__shfl_sync(0xffffffffu, kk, j0 + u) & 1023u);
+                                const float a = __shfl_sync(0xffffffffu, av, j0 + u);
                                 if (n != cur_n) {
                                     if (cur_n >= 0) {
                                         flush(first_run ? 0 : -1);
@@ -451,13 +480,17 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                                 }
                                 s1.x = fmaf(a, fm[u].x, s1.x);
                                 s1.y = fmaf(a, fm[u].y, s1.y);
-                                s2v.x = fmaf(a, fw[u].x, s2v.x);
-                                s2v.y = fmaf(a, fw[u].y, s2v.y);
-                                s2 += b2;
+                                if (AN) {
+                                    s2v.x = fmaf(a, fw[u].x, s2v.x);
+                                    s2v.y = fmaf(a, fw[u].y, s2v.y);
+                                } else {
+                                    s2 += __shfl_sync(0xffffffffu, v2, j0 + u);
+                                }
                             }
                         }
                     }
-                }
+                };
+                if (aniso) walk(std::true_type{}); else walk(std::false_type{});
                 if (cur_n >= 0) flush(first_run ? 0 : 1);
             }
             __syncthreads();
@@ -484,12 +517,29 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
         }
     }
     __syncthreads();
-    for (int n = warp; n < HW; n += 8) {
-        float* dst = g_xhat + ((size_t)b * HW + n) * D + d0;
-        const float* gr = G + (size_t)n * pitch;
-        const float* xr = xhat + ((size_t)b * HW + n) * D + d0;
-        const float gn = aniso ? 0.f : g2[n];                   // isotropic: - xhat_n * sum_e a_e w_p applied here
-        for (int d = lane; d < dc; d += 32) dst[d] = (gn != 0.f) ? fmaf(-gn, xr[d], gr[d]) : gr[d];
+    if ((dc & 3) == 0) {
+        const int q4 = dc >> 2;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < HW * q4; i += 256) {
+            const int n = i / q4, c4 = i - n * q4;
+            const size_t go = ((size_t)b * HW + n) * D + d0 + 4 * c4;
+            float4 v = *reinterpret_cast<const float4*>(G + (size_t)n * pitch + 4 * c4);
+            const float gn = aniso ? 0.f : g2[n];               // isotropic: - xhat_n * sum_e a_e w_p applied here
+            if (gn != 0.f) {
+                const float4 xr = __ldg(reinterpret_cast<const float4*>(xhat + go));
+                v.x = fmaf(-gn, xr.x, v.x); v.y = fmaf(-gn, xr.y, v.y);
+                v.z = fmaf(-gn, xr.z, v.z); v.w = fmaf(-gn, xr.w, v.w);
+            }
+            *reinterpret_cast<float4*>(g_xhat + go) = v;
+        }
+    } else {
+        for (int n = warp; n < HW; n += 8) {
+            float* dst = g_xhat + ((size_t)b * HW + n) * D + d0;
+            const float* gr = G + (size_t)n * pitch;
+            const float* xr = xhat + ((size_t)b * HW + n) * D + d0;
+            const float gn = aniso ? 0.f : g2[n];
+            for (int d = lane; d < dc; d += 32) dst[d] = (gn != 0.f) ? fmaf(-gn, xr[d], gr[d]) : gr[d];
+        }
     }
 }
 

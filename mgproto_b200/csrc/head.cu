@@ -120,6 +120,35 @@ __device__ __forceinline__ void warp_topT_sorted(const float* const (&rows)[NR],
     }
 }
 
+// Level 0 only (max and arg-max, ties -> smaller index) of NR rows: with labels the reference overwrites
+// levels >= 1 of every wrong-class prototype with level 0 (model.py:218-221), so only the K rows of the
+// image's own class need the full top-T.  ~40 instructions per row instead of ~540: the kernel becomes a
+// streaming read of log p.
+template <int R, int NR>
+__device__ __forceinline__ void warp_top1(const float* const (&rows)[NR], int rs, int HW, int lane,
+                                          float (&out_v)[NR], int (&out_i)[NR]) {
+    float x[NR][R];
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = lane + 32 * r;
+            x[i][r] = (j < HW) ? rows[i][(size_t)j * rs] : -INFINITY;
+        }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        float mv = x[i][0];
+        int mr = 0;
+#pragma unroll
+        for (int r = 1; r < R; ++r)
+            if (x[i][r] > mv) { mv = x[i][r]; mr = r; }
+        const unsigned key = (lane < HW) ? f2key(mv) : 0u;
+        const unsigned best = __reduce_max_sync(0xffffffffu, key);
+        out_i[i] = __reduce_min_sync(0xffffffffu, (key == best) ? lane + 32 * mr : 0x7fffffff);
+        out_v[i] = key2f(best);
+    }
+}
+
 // FROM_NP = false: logp is [B,P,HW] (one contiguous row per (image, prototype)).
 // FROM_NP = true : logp is [N,P] (the compute_log_prob / tensor-core layout): the CTA first stages the
 //                  [HW x CT*K] block of its image and classes in shared memory (each patch row is a contiguous
@@ -151,14 +180,44 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
     }
-    for (int pl0 = warp * NR; pl0 < npl; pl0 += 8 * NR) {
+    const long long g = (gt != nullptr) ? (long long)gt[b] : -1;
+    const bool labelled = (gt != nullptr);
+    const int rs = FROM_NP ? pitch : 1;
+    // rows [gl0, gl0 + K) of this CTA belong to the image's own class (-1: none here / no labels)
+    const int gl0 = (labelled && g >= c0 && g < c0 + nc) ? (int)(g - c0) * K : -1;
+    if (labelled) {
+        for (int pl0 = warp * NR; pl0 < npl; pl0 += 8 * NR) {
+            const float* rows[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int pl = min(pl0 + i, npl - 1);
+                rows[i] = FROM_NP ? (tile + pl) : (logp + ((size_t)b * P + c0 * K + pl) * HW);
+            }
+            float v[NR];
+            int ix[NR];
+            warp_top1<R, NR>(rows, rs, HW, lane, v, ix);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int pl = pl0 + i;
+                const bool own = gl0 >= 0 && pl >= gl0 && pl < gl0 + K;     // done with all levels below
+                if (pl < npl && !own && lane < T) {
+                    const int p = c0 * K + pl;
+                    const float e = expf(v[i]);  // ref model.py:215; levels >= 1 alias level 0 (ref :218-221)
+                    if (lane == 0) win[pl * T] = e;
+                    vals[((size_t)b * P + p) * T + lane] = e;
+                    idx[((size_t)b * P + p) * T + lane] = ix[i];
+                }
+            }
+        }
+    }
+    const int fb = labelled ? gl0 : 0, fe = labelled ? (gl0 >= 0 ? gl0 + K : -1) : npl;   // rows needing all T levels
+    for (int pl0 = fb + warp * NR; pl0 < fe; pl0 += 8 * NR) {
         const float* rows[NR];
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            const int pl = min(pl0 + i, npl - 1);              // surplus slots recompute the last row, not stored
+            const int pl = min(pl0 + i, fe - 1);               // surplus slots recompute the last row, not stored
             rows[i] = FROM_NP ? (tile + pl) : (logp + ((size_t)b * P + c0 * K + pl) * HW);
         }
-        const int rs = FROM_NP ? pitch : 1;
         float v[NR];
         int ix[NR];
         if (R <= 8) warp_topT_sorted<(R <= 8 ? R : 1), NR>(rows, rs, HW, T, lane, v, ix);
@@ -166,7 +225,7 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             const int pl = pl0 + i;
-            if (pl < npl && lane < T) {
+            if (pl < fe && lane < T) {
                 const int p = c0 * K + pl;
                 const float e = expf(v[i]);  // ref model.py:215
                 win[pl * T + lane] = e;
@@ -176,7 +235,6 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
         }
     }
     __syncthreads();
-    const long long g = (gt != nullptr) ? (long long)gt[b] : -1;
     for (int e = threadIdx.x; e < nc * T; e += blockDim.x) {
         const int cl = e / T, t = e - cl * T;
         const int c = c0 + cl;

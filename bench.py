@@ -157,18 +157,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([f.strip() for f in line.split(",")])
+            self.rows.append((time.time(), [f.strip() for f in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples inside the timed window [t0, t1]; a window shorter than a few sampling periods falls back to
+        every sample taken under load (warm-up + timed + end-to-end loops run the same step back to back)."""
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        inside = [r for t, r in ok if t0 is not None and t0 <= t <= t1]
+        window = "timed"
+        if len(inside) < 3:
+            inside, window = [r for _, r in ok], "warmup+timed+e2e (timed region shorter than 3 samples)"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active")
-                                                         for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in inside)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def build_model(dev, seed=0):
@@ -254,23 +260,24 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------
-    for i in range(W):
-        step(feats[i % N_ROT], gts[i % N_ROT])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        step(feats[i % N_ROT], gts[i % N_ROT])
+    barrier()
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_w0 = time.time()
     e0.record()
     for i in range(args.steps):
         step(feats[i % N_ROT], gts[i % N_ROT])
     e1.record()
     barrier()
+    t_w1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     tm = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -300,6 +307,7 @@ def main():
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     e2e_val = B * world * args.steps / (float(tm) / 1e3)
+    clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
 
     # ---- roofline of the log-likelihood kernel (timed alone, rank 0) --------------------------
     roof = None

@@ -20,64 +20,85 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
     int* ucount = sm;       // [B] unique rows of image b
     int* cls = sm + B;      // [B] class or -1
     int* wr_m = sm + 2 * B; // [B] rows accepted for the class if b is the class's first image, else -1
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        const long long c = gt[b];
-        if (c < 0 || c >= C) {
-            cls[b] = -1;
-            ucount[b] = 0;
-            for (int k = 0; k < K; ++k) plan[b * K + k] = -1;
-            continue;
-        }
-        cls[b] = (int)c;
-        const int32_t* top1g = top1_bk + (size_t)b * K;
-        int top1[64];                                         // K <= 64 (checked on the host)
-        for (int k = 0; k < K; ++k) top1[k] = top1g[k];
-        int u = 0;
-        for (int k = 0; k < K; ++k) {
-            const int v = top1[k];
-            bool first = true;
-            for (int k2 = 0; k2 < k; ++k2) first = first && (top1[k2] != v);
-            int rank = -1;
-            if (first) {
-                // ascending position among the distinct values (torch.unique order): count distinct smaller ones
-                rank = 0;
-                for (int k2 = 0; k2 < K; ++k2) {
-                    const int v2 = top1[k2];
-                    if (v2 < v) {
-                        bool f2 = true;
-                        for (int k3 = 0; k3 < k2; ++k3) f2 = f2 && (top1[k3] != v2);
-                        rank += f2 ? 1 : 0;
-                    }
-                }
-                ++u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (K <= 32) {
+        // warp per image, lane per prototype: duplicates by MATCH.ANY, rank among the distinct values by K shuffles
+        for (int b = warp; b < B; b += nwarp) {
+            const long long c = gt[b];
+            const bool okc = (c >= 0 && c < C);
+            const int v = (okc && lane < K) ? top1_bk[(size_t)b * K + lane] : (-1 - lane);
+            const unsigned m = __match_any_sync(0xffffffffu, v);
+            const bool first = okc && lane < K && (__ffs(m) - 1 == lane);
+            const unsigned fm = __ballot_sync(0xffffffffu, first);
+            int rank = 0;                                     // ascending position among the distinct values (torch.unique order)
+            for (int j = 0; j < K; ++j) {
+                const int vj = __shfl_sync(0xffffffffu, v, j);
+                rank += (((fm >> j) & 1u) && vj < v) ? 1 : 0;
             }
-            plan[b * K + k] = rank;
+            if (lane < K) plan[b * K + lane] = first ? rank : -1;
+            if (lane == 0) { cls[b] = okc ? (int)c : -1; ucount[b] = __popc(fm); }
         }
-        ucount[b] = u;
+    } else {
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const long long c = gt[b];
+            if (c < 0 || c >= C) {
+                cls[b] = -1;
+                ucount[b] = 0;
+                for (int k = 0; k < K; ++k) plan[b * K + k] = -1;
+                continue;
+            }
+            cls[b] = (int)c;
+            const int32_t* top1 = top1_bk + (size_t)b * K;
+            int u = 0;
+            for (int k = 0; k < K; ++k) {
+                const int v = top1[k];
+                bool first = true;
+                for (int k2 = 0; k2 < k; ++k2) first = first && (top1[k2] != v);
+                int rank = -1;
+                if (first) {
+                    rank = 0;
+                    for (int k2 = 0; k2 < K; ++k2) {
+                        const int v2 = top1[k2];
+                        if (v2 < v) {
+                            bool f2 = true;
+                            for (int k3 = 0; k3 < k2; ++k3) f2 = f2 && (top1[k3] != v2);
+                            rank += f2 ? 1 : 0;
+                        }
+                    }
+                    ++u;
+                }
+                plan[b * K + k] = rank;
+            }
+            ucount[b] = u;
+        }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    // warp per image: rows of the same class in earlier images (offset) and in the whole batch (total)
+    for (int b = warp; b < B; b += nwarp) {
         const int c = cls[b];
         if (c < 0) continue;
-        int off = 0, tot = 0;
-        bool first_of_class = true;
-        for (int b2 = 0; b2 < B; ++b2) {
+        int off = 0, tot = 0, earlier = 0;
+        for (int b2 = lane; b2 < B; b2 += 32) {
             if (cls[b2] == c) {
-                if (b2 < b) { off += ucount[b2]; first_of_class = false; }
-                tot += ucount[b2];
+                const int u = ucount[b2];
+                tot += u;
+                if (b2 < b) { off += u; earlier = 1; }
             }
         }
+        off = __reduce_add_sync(0xffffffffu, off);
+        tot = __reduce_add_sync(0xffffffffu, tot);
+        const bool first_of_class = __reduce_add_sync(0xffffffffu, earlier) == 0;
         const int len = (int)mem_len[c];
         const int hd = head[c];
         const int m = min(tot, cap);
-        for (int k = 0; k < K; ++k) {
+        for (int k = lane; k < K; k += 32) {
             const int r = plan[b * K + k];
             int slot = -1;
             if (r >= 0 && off + r < m) slot = (hd + len + off + r) % cap;
             plan[b * K + k] = slot;
         }
         // every reader of mem_len/head for class c sees the same old values; publish after the barrier
-        wr_m[b] = first_of_class ? m : -1;
+        if (lane == 0) wr_m[b] = first_of_class ? m : -1;
     }
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) {

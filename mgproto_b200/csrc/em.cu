@@ -694,20 +694,30 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
                 __syncthreads();
                 for (int s = tid; s < ns; s += 256) {
                     const double st = (double)(s0 + s + 1);
-                    const double b1s = pow((double)adam.beta1, st), b2s = pow((double)adam.beta2, st);
-                    const double b1t = pow((double)adam.beta1, (double)first + st);
-                    const double b2t = pow((double)adam.beta2, (double)first + st);
+                    const double l1 = log((double)adam.beta1), l2 = log((double)adam.beta2);
+                    const double b1s = exp(st * l1), b2s = exp(st * l2);
+                    const double b1t = exp(((double)first + st) * l1);
+                    const double b2t = exp(((double)first + st) * l2);
                     s_c[s] = (float)((double)adam.lr * b1s / (1.0 - b1t));
                     s_d[s] = (float)(sqrt(b2s) / sqrt(1.0 - b2t));
                 }
                 __syncthreads();
                 const int nel = min(8, (KD - ob + 255) / 256);         // elements this thread row actually owns
-                for (int s = 0; s < ns; ++s) {
-                    const float cs = -s_c[s], ds = s_d[s];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < nel) p_[i] = fmaf(cs * m0_[i], __fdividef(1.0f, fmaf(a_[i], ds, adam.eps)), p_[i]);
-                }
+                // one FMA + one MUFU.RCP + FMUL + FMA per (step, element); the element count is a compile-time
+                // constant of each branch (padding slots have m0 = 0, a = 1)
+#define MGP_REPLAY(NEL)                                                                                              \
+    for (int s = 0; s < ns; ++s) {                                                                                  \
+        const float cs = -s_c[s], ds = s_d[s];                                                                      \
+        _Pragma("unroll") for (int i = 0; i < NEL; ++i) {                                                           \
+            float rc;                                                                                               \
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.eps)));                          \
+            p_[i] = fmaf(cs * m0_[i], rc, p_[i]);                                                                   \
+        }                                                                                                           \
+    }
+                if (nel <= 3) { MGP_REPLAY(3) }
+                else if (nel <= 5) { MGP_REPLAY(5) }
+                else { MGP_REPLAY(8) }
+#undef MGP_REPLAY
             }
             const float mdec = (float)pow((double)adam.beta1, (double)count);
             const float vdec = (float)pow((double)adam.beta2, (double)count);
@@ -754,28 +764,47 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
     const float div_scale = -4.0f * lamda / ((float)K * (float)(K - 1));
     const int step = step0 + num_em_loop * ord + em_loop + 1;
     const double b1p = pow((double)adam.beta1, (double)step), b2p = pow((double)adam.beta2, (double)step);
-    for (int o = tid; o < KD; o += 256) {
-        const int k = o / D, d = o - k * D;
-        float s1 = 0.f;
-        for (int s = 0; s < n_split; ++s) s1 += stats[((size_t)c * n_split + s) * stat_stride + K + o];
-        const float sg = sigma[(size_t)c * KD + o] + EM_EPS;
-        const float w = 1.0f / (sg * sg);
-        const float muv = s_mu[o];
-        float g = -(s1 - muv * s_s0[k]) * w / n_rows;
-        float esum = 0.f, emu = 0.f;
-        for (int j = 0; j < K; ++j) {
-            const float e = s_e[k * K + j];
-            esum += e;
-            emu = fmaf(e, s_mu[j * D + d], emu);
+    // all global operands of up to 8 owned elements are fetched before any is used (the kernel is a chain of
+    // cold-miss latencies otherwise: ncu long_scoreboard 5.6 per issue)
+    for (int ob = 0; ob < KD; ob += 256 * 8) {
+        float s1_[8], sg_[8], m_[8], v_[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = ob + tid + 256 * i;
+            s1_[i] = 0.f; sg_[i] = 1.f; m_[i] = 0.f; v_[i] = 0.f;
+            if (o < KD) {
+                for (int sp = 0; sp < n_split; ++sp) s1_[i] += stats[((size_t)c * n_split + sp) * stat_stride + K + o];
+                sg_[i] = sigma[(size_t)c * KD + o];
+                if (do_adam) {
+                    m_[i] = exp_avg[(size_t)c * KD + o];
+                    v_[i] = exp_avg_sq[(size_t)c * KD + o];
+                }
+            }
         }
-        g += div_scale * (esum * muv - emu);
-        if (grad_out) grad_out[(size_t)c * KD + o] = g;
-        if (do_adam) {
-            float p = muv, m = exp_avg[(size_t)c * KD + o], v = exp_avg_sq[(size_t)c * KD + o];
-            adam_apply(p, m, v, g, adam, b1p, b2p);
-            mu_c[o] = p;
-            exp_avg[(size_t)c * KD + o] = m;
-            exp_avg_sq[(size_t)c * KD + o] = v;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = ob + tid + 256 * i;
+            if (o >= KD) continue;
+            const int k = o / D, d = o - k * D;
+            const float sg = sg_[i] + EM_EPS;
+            const float w = 1.0f / (sg * sg);
+            const float muv = s_mu[o];
+            float g = -(s1_[i] - muv * s_s0[k]) * w / n_rows;
+            float esum = 0.f, emu = 0.f;
+            for (int j = 0; j < K; ++j) {
+                const float e = s_e[k * K + j];
+                esum += e;
+                emu = fmaf(e, s_mu[j * D + d], emu);
+            }
+            g += div_scale * (esum * muv - emu);
+            if (grad_out) grad_out[(size_t)c * KD + o] = g;
+            if (do_adam) {
+                float p = muv, m = m_[i], v = v_[i];
+                adam_apply(p, m, v, g, adam, b1p, b2p);
+                mu_c[o] = p;
+                exp_avg[(size_t)c * KD + o] = m;
+                exp_avg_sq[(size_t)c * KD + o] = v;
+            }
         }
     }
     // pi <- tau*pi + (1-tau)*(S0 + eps)/n   (ref :385, :399, :297-298)

@@ -49,6 +49,10 @@ extern "C" {
 #define MGP_OUT_LOGP_NP 0      /* out[n*P + p]           = log p      (ref: compute_log_prob)   */
 #define MGP_OUT_LOGP_BPHW 1    /* out[(b*P + p)*HW + hw] = log p      (feeds mgp_head_select)    */
 #define MGP_OUT_NEGP_BPHW 2    /* out[(b*P + p)*HW + hw] = -exp(log p) (ref: push_forward :437)  */
+#define MGP_OUT_TOP1_BP 3      /* no log p output: `out` is uint64 [B,P], out[b*P + p] = packed
+                                  (max_hw log p, arg max) -- ((monotone key of the float) << 32) |
+                                  (0xffffffff - hw), ties -> smaller hw.  Tensor-core path only
+                                  (MGP_ERR_UNSUPPORTED otherwise); feeds mgp_head_select_top1    */
 
 int mgp_abi_version(void);
 const char* mgp_error_string(int code);
@@ -98,6 +102,21 @@ int mgp_head_select(const float* logp_bphw, const float* weight_cp, const int64_
 int mgp_head_select_np(const float* logp_np, const float* weight_cp, const int64_t* gt,
                        float* logits, float* vals, int32_t* idx, int B, int HW, int C, int K,
                        int T, void* stream);
+
+/* Labelled (training) variant that never materialises log p.  With labels the reference overwrites
+ * levels t >= 1 of every wrong-class prototype with level 0 (model.py:218-221), so only
+ * max/arg-max over the patches is needed for the C-1 other classes: `best` [B,P] uint64 is the
+ * MGP_OUT_TOP1_BP output of mgp_logprob_fwd.  The K prototypes of each image's own class get the
+ * full top-T from an exact fp32 evaluation of their K x HW log-likelihoods inside this call
+ * (xhat_nd [N,D], mu/sigma [P,D], eps = eps_log = 0 as in compute_log_prob).
+ * Outputs as mgp_head_select; of vals/idx [B,P,T] only level 0 (all prototypes) and levels
+ * 0..T-1 of the own-class prototypes are written -- exactly the entries the logits, the enqueue
+ * and mgp_head_bwd read when labels are given.  gt must not be NULL; gt[b] outside [0,C) makes
+ * every class of image b a wrong class. */
+int mgp_head_select_top1(const uint64_t* best, const float* xhat_nd, const float* mu,
+                         const float* sigma, const float* weight_cp, const int64_t* gt,
+                         float* logits, float* vals, int32_t* idx, int B, int HW, int C, int K,
+                         int D, int T, void* stream);
 
 /* Backward of mgp_head_select composed with the log-likelihood and the normalisation:
  * grad_logits [B,C,T] -> g_x_nchw [B,D,HW] (gradient w.r.t. the un-normalised features;

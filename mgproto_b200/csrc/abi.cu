@@ -49,7 +49,7 @@ extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const floa
                                size_t ws_bytes, void* stream) {
     if (!xhat_nd || !mu || !sigma || !out || !ws) return MGP_ERR_INVALID;
     if (B <= 0 || HW <= 0 || P <= 0 || D <= 0 || (D & 3)) return MGP_ERR_INVALID;
-    if (out_layout < MGP_OUT_LOGP_NP || out_layout > MGP_OUT_NEGP_BPHW) return MGP_ERR_INVALID;
+    if (out_layout < MGP_OUT_LOGP_NP || out_layout > MGP_OUT_TOP1_BP) return MGP_ERR_INVALID;
     if (!mgp_aligned16(xhat_nd) || !mgp_aligned16(mu) || !mgp_aligned16(sigma) || !mgp_aligned16(out) ||
         !mgp_aligned16(ws))
         return MGP_ERR_INVALID;
@@ -66,6 +66,7 @@ extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const floa
 #else
     if (math == MGP_MATH_TC || math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO) return MGP_ERR_UNSUPPORTED;
 #endif
+    if (out_layout == MGP_OUT_TOP1_BP) return MGP_ERR_UNSUPPORTED;   // fused max/arg-max exists on the tensor-core path only
     return mgp_logprob_simt_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D,
                                    reinterpret_cast<float*>(ws), st);
 }

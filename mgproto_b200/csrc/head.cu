@@ -6,15 +6,6 @@
 
 namespace {
 
-__device__ __forceinline__ unsigned f2key(float f) {  // monotone float -> uint (larger float = larger key)
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key2f(unsigned k) {
-    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return __uint_as_float(u);
-}
-
 // One warp selects the T largest of NR [HW] rows at once (descending, ties -> smaller index).
 // Each lane keeps R = ceil(HW/32) keys per row in registers; per level: warp REDUX.max on the lanes'
 // local maxima, REDUX.min on the index among equal maxima, winner removed from its lane.  The NR rows
@@ -242,6 +233,109 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
         const float* wrow = weight + (size_t)c * P + (size_t)c * K;            // class-diagonal block of last_layer.weight
         float s = 0.f;
         for (int k = 0; k < K; ++k) s = fmaf(__ldg(wrow + k), win[(cl * K + k) * T + (fold ? 0 : t)], s);
+        logits[((size_t)b * C + c) * T + t] = logf(s);                         // ref model.py:222, :254
+    }
+}
+
+// Labelled head without the log-likelihood matrix (mgp_head_select_top1).  grid B, block 256.
+//   1. level 0 of every prototype from the packed (max, arg max) the tensor-core epilogue left in `best`
+//   2. the image's own class: exact fp32 log p of its K prototypes over the HW patches (thread per patch,
+//      prototype rows broadcast from shared memory), then the usual warp top-T on those K rows
+//   3. logits (wrong classes: every level = level 0, ref model.py:218-221)
+template <int R, int NR>
+__global__ void __launch_bounds__(256)
+head_top1_kernel(const unsigned long long* __restrict__ best, const float* __restrict__ xhat,
+                 const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ weight,
+                 const int64_t* __restrict__ gt, float* __restrict__ logits, float* __restrict__ vals,
+                 int32_t* __restrict__ idx, int HW, int C, int K, int D, int T) {
+    extern __shared__ __align__(16) float sm[];
+    const int P = C * K;
+    const int HWp = HW + 1;
+    float* win0 = sm;                    // [P]      exp(level-0 log p)
+    float* winT = win0 + P;              // [K][T]   own class, all levels
+    float* lp = winT + K * T;            // [K][HWp] own-class log p rows
+    float* s_mu = sm + ((P + K * T + K * HWp + 3) & ~3);   // [K][D], 16-byte aligned
+    float* s_ri = s_mu + K * D;          // [K][D]   1/sigma
+    float* s_ls = s_ri + K * D;          // [K]      sum_d log sigma
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long g = gt[b];
+    const bool gok = (g >= 0 && g < C);
+
+    for (int p = threadIdx.x; p < P; p += 256) {
+        const unsigned long long pk = best[(size_t)b * P + p];
+        const float e = expf(key2f((unsigned)(pk >> 32)));                       // ref model.py:215
+        win0[p] = e;
+        vals[((size_t)b * P + p) * T] = e;
+        idx[((size_t)b * P + p) * T] = (int)(0xffffffffu - (unsigned)(pk & 0xffffffffull));
+    }
+    if (gok) {
+        const float* mug = mu + (size_t)g * K * D;
+        const float* sgg = sigma + (size_t)g * K * D;
+        for (int i = threadIdx.x; i < K * D; i += 256) {
+            s_mu[i] = mug[i];
+            s_ri[i] = 1.0f / sgg[i];
+        }
+        for (int k = warp; k < K; k += 8) {
+            float ls = 0.f;
+            for (int d = lane; d < D; d += 32) ls += logf(sgg[k * D + d]);
+            ls = warp_sum(ls);
+            if (lane == 0) s_ls[k] = ls;
+        }
+        __syncthreads();
+        // log p[n,k] = -D/2 log 2pi - sum log sigma - 1/2 sum ((x-mu)/sigma)^2   (ref model.py:256-275, exact form)
+        for (int n = threadIdx.x; n < HW; n += 256) {
+            const float4* xr = reinterpret_cast<const float4*>(xhat + ((size_t)b * HW + n) * D);
+            for (int k0 = 0; k0 < K; k0 += 5) {
+                float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int d4 = 0; d4 < D / 4; ++d4) {
+                    const float4 xv = __ldg(xr + d4);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int k = min(k0 + i, K - 1);
+                        const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + 4 * d4);
+                        const float4 r = *reinterpret_cast<const float4*>(s_ri + k * D + 4 * d4);
+                        float t;
+                        t = (xv.x - m.x) * r.x; q[i] = fmaf(t, t, q[i]);
+                        t = (xv.y - m.y) * r.y; q[i] = fmaf(t, t, q[i]);
+                        t = (xv.z - m.z) * r.z; q[i] = fmaf(t, t, q[i]);
+                        t = (xv.w - m.w) * r.w; q[i] = fmaf(t, t, q[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    if (k0 + i < K) lp[(k0 + i) * HWp + n] = -0.5f * (float)D * MGP_LOG_2PI - s_ls[k0 + i] - 0.5f * q[i];
+            }
+        }
+        __syncthreads();
+        for (int k0 = warp * NR; k0 < K; k0 += 8 * NR) {
+            const float* rows[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) rows[i] = lp + min(k0 + i, K - 1) * HWp;
+            float v[NR];
+            int ix[NR];
+            if (R <= 8) warp_topT_sorted<(R <= 8 ? R : 1), NR>(rows, 1, HW, T, lane, v, ix);
+            else warp_topT<R, NR>(rows, 1, HW, T, lane, v, ix);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int k = k0 + i;
+                if (k < K && lane < T) {
+                    const int p = (int)g * K + k;
+                    const float e = expf(v[i]);
+                    winT[k * T + lane] = e;
+                    vals[((size_t)b * P + p) * T + lane] = e;
+                    idx[((size_t)b * P + p) * T + lane] = ix[i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < C * T; e += 256) {
+        const int c = e / T, t = e - c * T;
+        const float* wrow = weight + (size_t)c * P + (size_t)c * K;            // class-diagonal block of last_layer.weight
+        const bool own = gok && (long long)c == g;
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s = fmaf(__ldg(wrow + k), own ? winT[k * T + t] : win0[c * K + k], s);
         logits[((size_t)b * C + c) * T + t] = logf(s);                         // ref model.py:222, :254
     }
 }
@@ -715,6 +809,34 @@ extern "C" int mgp_head_select(const float* logp_bphw, const float* weight_cp, c
 extern "C" int mgp_head_select_np(const float* logp_np, const float* weight_cp, const int64_t* gt, float* logits,
                                   float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream) {
     return head_select_launch(logp_np, 1, weight_cp, gt, logits, vals, idx, B, HW, C, K, T, stream);
+}
+
+extern "C" int mgp_head_select_top1(const uint64_t* best, const float* xhat_nd, const float* mu, const float* sigma,
+                                    const float* weight_cp, const int64_t* gt, float* logits, float* vals, int32_t* idx,
+                                    int B, int HW, int C, int K, int D, int T, void* stream) {
+    if (!best || !xhat_nd || !mu || !sigma || !weight_cp || !gt || !logits || !vals || !idx) return MGP_ERR_INVALID;
+    if (B <= 0 || HW <= 0 || C <= 0 || K <= 0 || D <= 0 || T <= 0 || (D & 3)) return MGP_ERR_INVALID;
+    if (T > 32 || T > HW || HW > 1024) return MGP_ERR_UNSUPPORTED;
+    const int P = C * K;
+    const size_t smem = ((size_t)P + (size_t)K * T + (size_t)K * (HW + 1) + (size_t)2 * K * D + K + 4) * sizeof(float);
+    if (smem > 200 * 1024) return MGP_ERR_UNSUPPORTED;
+    const int R = (HW + 31) / 32;
+    cudaStream_t st = (cudaStream_t)stream;
+#define MGP_LAUNCH_T1(RR, NRR)                                                                                       \
+    do {                                                                                                             \
+        MGP_CUDA(cudaFuncSetAttribute(head_top1_kernel<RR, NRR>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)smem));                                                                   \
+        head_top1_kernel<RR, NRR><<<B, 256, smem, st>>>(reinterpret_cast<const unsigned long long*>(best), xhat_nd,  \
+                                                        mu, sigma, weight_cp, gt, logits, vals, idx, HW, C, K, D, T); \
+    } while (0)
+    if (R <= 4) MGP_LAUNCH_T1(4, 2);
+    else if (R <= 7) MGP_LAUNCH_T1(7, 2);
+    else if (R <= 13) MGP_LAUNCH_T1(13, 1);
+    else if (R <= 25) MGP_LAUNCH_T1(25, 1);
+    else MGP_LAUNCH_T1(32, 1);
+#undef MGP_LAUNCH_T1
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
 }
 
 extern "C" size_t mgp_head_bwd_ws_bytes(int B, int HW, int P, int D) {

@@ -36,6 +36,7 @@ constexpr int NT_MAX = 256;      // patches per tile (UMMA N): 256 (192 with the
 constexpr int LAYOUT_NP_TMA = 3; // internal: [N,P] output written by TMA bulk tensor stores from a shared-memory stage
 constexpr int LAYOUT_BPHW_TMA = 4;   // internal: [B,P,HW] log p through a 3-D tensor map (boxes clipped at image ends)
 constexpr int LAYOUT_NEGP_TMA = 5;   // internal: [B,P,HW] -exp(log p), same
+constexpr int LAYOUT_TOP1 = 6;       // internal: no log p output at all -- per (image, prototype) max / arg-max (MGP_OUT_TOP1_BP)
 constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // one [32 patches x 32 prototypes] fp32 block per epilogue warp
 constexpr int PT = 128;          // prototypes per tile (UMMA M)
 constexpr int KB = 64;           // K elements per smem block (128 B rows, SWIZZLE_128B)
@@ -250,7 +251,8 @@ template <int LAYOUT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const float* __restrict__ s_sn_c, float c0,
                                                float c1, float c2, int n0, int p, bool pok, const TcParams& prm,
                                                float* stg = nullptr, const CUtensorMap* map_out = nullptr, int img_b = 0,
-                                               int img_hw0 = 0) {
+                                               int img_hw0 = 0, bool img = false, float* run_v = nullptr,
+                                               int* run_i = nullptr) {
     const int N = prm.N, P = prm.P, HW = prm.HW;
     float v[32];
     const float4* s4 = reinterpret_cast<const float4*>(s_sn_c);    // |x_n|^2 of the 32 columns (shared memory)
@@ -261,6 +263,42 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
         v[4 * j4 + 1] = fmaf(c1, __uint_as_float(r[4 * j4 + 1]), fmaf(c2, s.y, c0));
         v[4 * j4 + 2] = fmaf(c1, __uint_as_float(r[4 * j4 + 2]), fmaf(c2, s.z, c0));
         v[4 * j4 + 3] = fmaf(c1, __uint_as_float(r[4 * j4 + 3]), fmaf(c2, s.w, c0));
+    }
+    if (LAYOUT == LAYOUT_TOP1) {
+        // only max_n log p[n, p] and its patch per image are wanted (labelled training step: the reference aliases
+        // the other levels of wrong-class prototypes to level 0): nothing is stored, the log-likelihood matrix
+        // never reaches HBM.  Image tiles keep a running (max, patch) across the warp's chunks (the caller issues
+        // one 64-bit RED.MAX per tile); 128-patch tiles may cross image ends and reduce per image segment.
+        if (img) {
+            float mv = *run_v;
+            int mi = *run_i;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const bool better = (img_hw0 + j < HW) && (v[j] > mv);
+                mv = better ? v[j] : mv;
+                mi = better ? img_hw0 + j : mi;
+            }
+            *run_v = mv;
+            *run_i = mi;
+            return;
+        }
+        if (!pok) return;
+        unsigned long long* best = reinterpret_cast<unsigned long long*>(prm.out);
+        int b = n0 / HW, hw = n0 - b * HW;
+        float mv = -INFINITY;
+        int mi = -1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (n0 + j < N) {
+                if (mi < 0 || v[j] > mv) { mv = v[j]; mi = hw; }
+                if (++hw == HW) {
+                    atomicMax(best + (size_t)b * P + p, top1_pack(mv, mi));
+                    ++b; hw = 0; mi = -1;
+                }
+            }
+        }
+        if (mi >= 0) atomicMax(best + (size_t)b * P + p, top1_pack(mv, mi));
+        return;
     }
     if (LAYOUT == LAYOUT_NP_TMA) {
         // stage the [32 patches x 32 prototypes] block in shared memory (row = patch, 128 B) and hand it to
@@ -365,7 +403,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     // [B,P,HW] through TMA: one x tile = one image (nti = round_up(HW,32) columns, UMMA N = nti) so that no
     // 32-column chunk crosses an image end.  The wider tile only fits when sigma is isotropic (K = D);
     // otherwise this instantiation falls back to 128-patch tiles and register stores.
-    const bool img = BPHW_TMA && !gen;
+    const bool img = (BPHW_TMA || (LAYOUT == LAYOUT_TOP1 && prm.xbox == 32)) && !gen;
     const int NT = img ? prm.nti : 128;                           // patches per tile = UMMA N
     const int row_step = img ? prm.HW : 128;                      // first patch row of x tile nt = nt * row_step
     const uint32_t idesc = make_idesc(NT);
@@ -525,6 +563,8 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                 tc_fence_after();
                 if (!skip_epi) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT);
+                    float run_v = -INFINITY;                      // LAYOUT_TOP1, image tiles: best of this warp's chunks
+                    int run_i = -1;
 #pragma unroll 1
                     for (int ch = ch0; ch < ch1; ch += 2) {
                         uint32_t r0[32], r1[32];
@@ -544,16 +584,19 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
                         }
                         if (!BPHW_TMA || img) {
                             epilogue_chunk<LAYOUT>(r0, s_sn + ch * 32, c0, c1, c2, row0 + ch * 32, p, pok, prm, stg, &map_out,
-                                                   nt, ch * 32);
+                                                   nt, ch * 32, img, &run_v, &run_i);
                             if (two)
                                 epilogue_chunk<LAYOUT>(r1, s_sn + (ch + 1) * 32, c0, c1, c2, row0 + (ch + 1) * 32, p, pok, prm,
-                                                       stg, &map_out, nt, (ch + 1) * 32);
+                                                       stg, &map_out, nt, (ch + 1) * 32, img, &run_v, &run_i);
                         } else {
                             epilogue_chunk<STG_LAYOUT>(r0, s_sn + ch * 32, c0, c1, c2, row0 + ch * 32, p, pok, prm);
                             if (two)
                                 epilogue_chunk<STG_LAYOUT>(r1, s_sn + (ch + 1) * 32, c0, c1, c2, row0 + (ch + 1) * 32, p, pok, prm);
                         }
                     }
+                    if (LAYOUT == LAYOUT_TOP1 && img && pok && run_i >= 0 && !(prm.debug & 1))
+                        atomicMax(reinterpret_cast<unsigned long long*>(prm.out) + (size_t)nt * prm.P + p,
+                                  top1_pack(run_v, run_i));
                     if (ch0 >= ch1) {                             // (never for NT >= 64; keeps the barrier count right)
                         tc_fence_before();
                         __syncwarp();
@@ -702,12 +745,16 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     const bool tma_np = (layout == MGP_OUT_LOGP_NP) && (P % 4 == 0) && tma_ok;
     // [B,P,HW] through the 3-D map uses image-aligned x tiles (a chunk may not cross an image end)
     const bool tma_bphw = (layout != MGP_OUT_LOGP_NP) && (HW % 4 == 0) && HW >= 32 && HW <= 256 && tma_ok && D <= 128;
-    const bool tma_store = tma_np || tma_bphw;
-    const uint32_t xbox = tma_bphw ? 32u : 128u;
+    const bool top1 = (layout == MGP_OUT_TOP1_BP);
+    const bool tma_store = (tma_np || tma_bphw) && !top1;
+    // image-aligned x tiles (box of 32 rows) for the [B,P,HW] TMA stores and for the top-1 epilogue
+    const bool img_tiles = (tma_bphw && !top1) || (top1 && HW >= 32 && HW <= 256 && D <= 128);
+    const uint32_t xbox = img_tiles ? 32u : 128u;
+    if (top1) MGP_CUDA(cudaMemsetAsync(out, 0, (size_t)B * P * sizeof(unsigned long long), st));
     if (!make_map(&mxh, ah, (uint64_t)N, 2 * D, xbox) || !make_map(&mxl, al, (uint64_t)N, 2 * D, xbox) ||
         !make_map(&mph, bh, (uint64_t)P, 2 * D, 128) || !make_map(&mpl, bl, (uint64_t)P, 2 * D, 128))
         return MGP_ERR_UNSUPPORTED;
-    if (tma_bphw) {
+    if (tma_bphw && !top1) {
         if (!make_out_map_bphw(&mout, out, (uint64_t)B, (uint64_t)P, (uint64_t)HW)) return MGP_ERR_UNSUPPORTED;
     } else if (!make_out_map(&mout, tma_np ? out : (float*)ah, tma_np ? (uint64_t)N : 64, tma_np ? (uint64_t)P : 64)) {
         return MGP_ERR_UNSUPPORTED;
@@ -738,7 +785,7 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     if (team > sms) team = sms;
     int n_teams = sms / team;
     {
-        const int nt_min = (tma_bphw && B < prm.n_ntiles) ? B : prm.n_ntiles;
+        const int nt_min = (img_tiles && B < prm.n_ntiles) ? B : prm.n_ntiles;
         if (n_teams > nt_min) n_teams = nt_min;
     }
     prm.team = team;
@@ -755,7 +802,8 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
         MGP_CUDA(cudaFuncSetAttribute(logprob_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         logprob_tc_kernel<L><<<grid, TC_THREADS, smem, st>>>(mxh, mxl, mph, mpl, mout, prm);                               \
     } while (0)
-    if (tma_np) MGP_TC_LAUNCH(LAYOUT_NP_TMA);
+    if (top1) MGP_TC_LAUNCH(LAYOUT_TOP1);
+    else if (tma_np) MGP_TC_LAUNCH(LAYOUT_NP_TMA);
     else if (tma_bphw && layout == MGP_OUT_LOGP_BPHW) MGP_TC_LAUNCH(LAYOUT_BPHW_TMA);
     else if (tma_bphw) MGP_TC_LAUNCH(LAYOUT_NEGP_TMA);
     else if (layout == MGP_OUT_LOGP_NP) MGP_TC_LAUNCH(MGP_OUT_LOGP_NP);

@@ -32,3 +32,17 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// monotone float <-> uint keys (larger float = larger key; 0 sorts below every float incl. -inf)
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+// (value, patch) packed so that a 64-bit max picks the larger value and, among equal values, the smaller patch
+__device__ __forceinline__ unsigned long long top1_pack(float v, int hw) {
+    return ((unsigned long long)f2key(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)hw);
+}

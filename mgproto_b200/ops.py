@@ -10,9 +10,9 @@ import torch
 
 from . import _lib
 from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, MGP_MATH_TC_REUSE, MGP_OUT_LOGP_BPHW,
-                   MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, check)
+                   MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP, check)
 
-__all__ = ["normalize_fwd", "logprob", "head_select", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
+__all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
            "bank_linearize", "em_plan", "em_stats", "em_update", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
@@ -123,6 +123,53 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
     return (out, ws) if return_ws else out
 
 
+def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto"):
+    """Per (image, prototype) max / arg-max of log p over the patches, computed in the tensor-core kernel's
+    epilogue without writing log p (MGP_OUT_TOP1_BP).  -> packed int64 [B,P] (see include/mgproto_b200.h), or None
+    when the tensor-core path does not cover the shape / math mode (the caller then materialises log p)."""
+    x = _req(xhat_nd, torch.float32, "xhat")
+    mu = _req(mu_pd, torch.float32, "mu")
+    sg = _req(sigma_pd, torch.float32, "sigma")
+    N, D = x.shape
+    P = mu.shape[0]
+    if B * HW != N or mu.shape != (P, D) or sg.shape != (P, D):
+        raise RuntimeError("mgproto_b200: shape mismatch in logprob_top1")
+    m = _math(math)
+    if m == MGP_MATH_AUTO and D > 128:
+        m = MGP_MATH_TC_ISO if (D == 256 and sigma_is_isotropic(sg)) else MGP_MATH_FP32
+    if m == MGP_MATH_FP32 or m == MGP_MATH_TC_REUSE:
+        return None
+    lib = _lib.load()
+    nbytes = lib.mgp_logprob_ws_bytes(B, HW, P, D, m)
+    ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
+    best = torch.empty((B, P), device=x.device, dtype=torch.int64)
+    rc = lib.mgp_logprob_fwd(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), 0.0, 0.0, best.data_ptr(), MGP_OUT_TOP1_BP,
+                             B, HW, P, D, m, ws.data_ptr(), nbytes, _stream())
+    if rc == -2:                                      # MGP_ERR_UNSUPPORTED: no tensor-core path for this shape
+        return None
+    check(rc, "mgp_logprob_fwd(top1)")
+    _count(4)
+    return best
+
+
+def head_select_top1(best, xhat_nd, mu_pd, sigma_pd, weight_cp, gt, T, C, K, HW):
+    """Labelled head from the packed level-0 results (ref model.py:188-206, :218-222, :254): full top-T only for
+    every image's own class (exact fp32 log p of its K prototypes).  -> (logits [B,C,T], vals, idx [B,P,T]);
+    of vals/idx only level 0 and the own-class rows are written."""
+    B, P = best.shape
+    x = _req(xhat_nd, torch.float32, "xhat")
+    D = x.shape[1]
+    gt = _req(gt, torch.int64, "gt")
+    logits = torch.empty((B, C, T), device=x.device, dtype=torch.float32)
+    vals = torch.empty((B, P, T), device=x.device, dtype=torch.float32)
+    idx = torch.empty((B, P, T), device=x.device, dtype=torch.int32)
+    check(_lib.load().mgp_head_select_top1(best.data_ptr(), x.data_ptr(), mu_pd.data_ptr(), sigma_pd.data_ptr(),
+                                           weight_cp.data_ptr(), gt.data_ptr(), logits.data_ptr(), vals.data_ptr(),
+                                           idx.data_ptr(), B, HW, C, K, D, T, _stream()), "mgp_head_select_top1")
+    _count(1)
+    return logits, vals, idx
+
+
 # ----------------------------------------------------------------------------------- a4-a7
 def head_select(logp, weight_cp, gt, T, C, K, B=None, HW=None):
     """ref model.py:188-206, :218-222, :254 -> (logits [B,C,T], vals [B,P,T], idx [B,P,T] int32).
@@ -172,8 +219,13 @@ class HeadFunction(torch.autograd.Function):
         sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
         wt = weight_cp.detach().contiguous()
         xhat, inv, _ = normalize_fwd(x_add)
-        lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)   # [B,P,HW]: contiguous rows for the mining
-        logits, vals, idx = head_select(lp, wt, gt, T, C, K)
+        best = logprob_top1(xhat, mu, sg, B, HW, math) if (gt is not None and T <= min(32, HW)) else None
+        if best is not None:
+            # labelled step: log p never reaches HBM (wrong-class prototypes only need their max, ref model.py:218-221)
+            logits, vals, idx = head_select_top1(best, xhat, mu, sg, wt, _req(gt, torch.int64, "gt"), T, C, K, HW)
+        else:
+            lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)   # [B,P,HW]: contiguous rows for the mining
+            logits, vals, idx = head_select(lp, wt, gt, T, C, K)
         ctx.save_for_backward(logits, vals, idx, wt, gt if gt is not None else torch.empty(0), xhat, inv, mu, sg)
         ctx.has_gt = gt is not None
         ctx.dims = (B, HW, C, K, D, T, H, W)

@@ -480,3 +480,69 @@ def test_push_prototypes_matches_oracle():
         assert res["patch"][j] == oi[i, k]
         hh, ww = divmod(int(oi[i, k]), W)
         np.testing.assert_allclose(net.prototype_means[c, k].detach().cpu().numpy(), feat[i, :, hh, ww], rtol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C,K,D,T,aniso", [(5, 14, 14, 7, 10, 128, 20, False), (3, 7, 7, 5, 4, 64, 6, False),
+                                                 (4, 4, 4, 3, 5, 64, 4, False), (3, 14, 14, 4, 10, 128, 20, True),
+                                                 (2, 16, 16, 3, 3, 128, 32, False)])
+def test_fused_top1_path_vs_materialised(B, H, W, C, K, D, T, aniso):
+    """Labelled head: the tensor-core epilogue's packed max/arg-max (MGP_OUT_TOP1_BP) + mgp_head_select_top1 against
+    the path that materialises log p [B,P,HW] and mines it (mgp_head_select), and against fp64."""
+    from mgproto_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + D + T)
+    HW, P = H * W, C * K
+    x = torch.randn(B, D, H, W, generator=g).to(_dev())
+    mu = F.normalize(torch.rand(C, K, D, generator=g), dim=2).to(_dev())
+    sg = torch.full((C, K, D), 1 / np.sqrt(2 * np.pi))
+    if aniso:
+        sg = sg * (0.8 + 0.4 * torch.rand(C, K, D, generator=g))
+    sg = sg.to(_dev())
+    pi = torch.softmax(torch.randn(C, K, generator=g), dim=1)
+    wt = torch.zeros(C, P)
+    for c in range(C):
+        wt[c, c * K:(c + 1) * K] = pi[c]
+    wt = wt.to(_dev())
+    gt = torch.randint(0, C, (B,), generator=g).to(_dev())
+    gt[0] = -1 if B > 2 else gt[0]                      # an image without a valid class: every class is "wrong"
+    xhat, _, _ = ops.normalize_fwd(x)
+    mu2, sg2 = mu.reshape(P, D).contiguous(), sg.reshape(P, D).contiguous()
+    best = ops.logprob_top1(xhat, mu2, sg2, B, HW, "tc")
+    assert best is not None
+    xd = xhat.double().reshape(B, HW, D)
+    lp64 = (-0.5 * D * np.log(2 * np.pi) - sg2.double().log().sum(-1).view(1, 1, P)
+            - 0.5 * (((xd[:, :, None, :] - mu2.double().view(1, 1, P, D)) / sg2.double().view(1, 1, P, D)) ** 2).sum(-1))
+    lp64 = lp64.permute(0, 2, 1)                                               # [B,P,HW]
+    bv = best.cpu().numpy().astype(np.uint64)
+    key = (bv >> np.uint64(32)).astype(np.uint32)
+    u = np.where(key & np.uint32(0x80000000), key & np.uint32(0x7fffffff), ~key).astype(np.uint32)
+    val = u.view(np.float32)
+    arg = (np.uint32(0xffffffff) - (bv & np.uint64(0xffffffff)).astype(np.uint32)).astype(np.int64)
+    m64, a64 = lp64.max(dim=2)
+    np.testing.assert_allclose(val, m64.cpu().numpy(), rtol=RTOL, atol=1e-4)
+    srt = torch.sort(lp64, dim=2, descending=True).values
+    sep = ((srt[:, :, 0] - srt[:, :, 1]) > 1e-3).cpu().numpy()
+    assert (arg[sep] == a64.cpu().numpy()[sep]).all()
+    # whole head, both routes
+    lg1, v1, i1 = ops.head_select_top1(best, xhat, mu2, sg2, wt, gt, T, C, K, HW)
+    lp = ops.logprob(xhat, mu2, sg2, 1, B=B, HW=HW, math="tc")
+    lg0, v0, i0 = ops.head_select(lp, wt, gt, T, C, K)
+    torch.testing.assert_close(lg1, lg0, rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(v1[:, :, 0], v0[:, :, 0], rtol=RTOL, atol=1e-30)
+    for b in range(B):
+        c = int(gt[b])
+        if c < 0:
+            continue
+        rows = slice(c * K, (c + 1) * K)
+        torch.testing.assert_close(v1[b, rows], v0[b, rows], rtol=RTOL, atol=1e-30)
+        s = torch.sort(lp64[b, rows], dim=1, descending=True).values[:, :T + 1]
+        okm = ((s[:, :-1] - s[:, 1:]) > 1e-3).cpu().numpy()
+        ref_i = torch.topk(lp64[b, rows], T, dim=1).indices.cpu().numpy()
+        assert (i1[b, rows].cpu().numpy()[okm] == ref_i[okm]).all()
+    # through autograd (the route HeadFunction takes with labels) against the materialised route's gradient
+    xa = x.clone().requires_grad_(True)
+    out, _, _ = ops.head_forward(xa, mu, sg, wt, gt, T, "tc")
+    gl = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).to(_dev())
+    out.backward(gl)
+    torch.testing.assert_close(out.detach(), lg0, rtol=RTOL, atol=1e-6)
+    assert torch.isfinite(xa.grad).all()

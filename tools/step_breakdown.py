@@ -89,6 +89,29 @@ def main():
     stats = torch.empty(C, net.em_n_split, ops.em_stat_stride(K, D), device=dev)
     res["em_stats"] = timeit(lambda: ops.em_stats(net.queue.bank, order, net.prototype_means.data,
                                                   net.prototype_covs.data, wt, 0.1, stats, net.em_n_split))
+    # host cost of enqueueing one whole step (python + ctypes + autograd), GPU kept busy so nothing blocks:
+    # if this exceeds the device time per step the loop is launch-bound
+    import time
+
+    def step():
+        xr.grad = None
+        out = net.head(xr, gt)
+        bench.loss_fn(out, gt).backward()
+        net.update_GMM()
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    n = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    t1 = time.perf_counter()
+    e1.record()
+    torch.cuda.synchronize()
+    res["step_host_enqueue_us"] = (t1 - t0) / n * 1e6
+    res["step_device_us"] = e0.elapsed_time(e1) / n * 1e3
     print(json.dumps(res, indent=1))
 
 

@@ -197,6 +197,17 @@ int mgp_em_update(const float* stats, int n_split, int with_s2, int n_rows_total
                   float tau, float lamda, float* grad_out, int only_class, int C, int K, int D,
                   void* stream);
 
+/* The whole update_GMM (ref model.py:277-301) of a single-GPU replica in one call: mgp_em_plan (with the
+ * device-resident Adam step counter adam_step[0]), phase 0, num_em_loop x (mgp_em_stats over all cap rows,
+ * phase 1), phase 2 -- 3 + 2*num_em_loop launches enqueued on `stream`, nothing read back.  order [C] int32,
+ * sched [2] int32 and stats [C][n_split][mgp_em_stat_stride(K,D,0)] fp32 are scratch.  (A batch-sharded
+ * multi-GPU caller uses the individual entry points, with an all-reduce of stats between the two.) */
+int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t* mem_len, float* mu,
+                   const float* sigma, float* weight_cp, float* exp_avg, float* exp_avg_sq,
+                   int32_t* adam_step, int32_t* order, int32_t* sched, float* stats, int n_split,
+                   int num_em_loop, float alpha, float lr, float beta1, float beta2, float adam_eps,
+                   float tau, float lamda, int C, int K, int D, int cap, void* stream);
+
 /* ---- a11/a13/a14  EM building blocks on explicit rows ---------------------------------------
  * ref: model.py:303-321 (_e_step), :338-365 (_m_step), :403-421 (_score).
  * x [n,D], mu/sigma [K,D], pi [K]  ->  log_resp [n,K], score [n] = logsumexp_k(lp+log(pi+1e-10)).

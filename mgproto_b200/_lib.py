@@ -34,6 +34,7 @@ SIGNATURES = {
     "mgp_bank_enqueue": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
     "mgp_bank_linearize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_stat_stride": (_sz, [_i, _i, _i]),
+    "mgp_update_gmm": (_i, [_vp] * 12 + [_i, _i] + [_f] * 7 + [_i] * 4 + [_vp]),
     "mgp_em_plan": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mgp_em_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "mgp_em_update": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,

@@ -1000,6 +1000,30 @@ extern "C" int mgp_em_update(const float* stats, int n_split, int with_s2, int n
     return MGP_OK;
 }
 
+extern "C" int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t* mem_len, float* mu, const float* sigma,
+                              float* weight_cp, float* exp_avg, float* exp_avg_sq, int32_t* adam_step, int32_t* order,
+                              int32_t* sched, float* stats, int n_split, int num_em_loop, float alpha, float lr,
+                              float beta1, float beta2, float adam_eps, float tau, float lamda, int C, int K, int D,
+                              int cap, void* stream) {
+    if (!bank || !updated || !mem_len || !mu || !sigma || !weight_cp || !exp_avg || !exp_avg_sq || !adam_step ||
+        !order || !sched || !stats)
+        return MGP_ERR_INVALID;
+    int rc = mgp_em_plan(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop, stream);
+    if (rc != MGP_OK) return rc;
+    rc = mgp_em_update(nullptr, n_split, 0, cap, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq, 0, num_em_loop,
+                       0, lr, beta1, beta2, adam_eps, tau, lamda, nullptr, -1, C, K, D, stream);
+    if (rc != MGP_OK) return rc;
+    for (int i = 0; i < num_em_loop; ++i) {
+        rc = mgp_em_stats(bank, order, mu, sigma, weight_cp, alpha, 0, cap, n_split, 0, stats, C, K, D, cap, stream);
+        if (rc != MGP_OK) return rc;
+        rc = mgp_em_update(stats, n_split, 0, cap, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq, i,
+                           num_em_loop, 1, lr, beta1, beta2, adam_eps, tau, lamda, nullptr, -1, C, K, D, stream);
+        if (rc != MGP_OK) return rc;
+    }
+    return mgp_em_update(nullptr, n_split, 0, cap, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq, 0,
+                         num_em_loop, 2, lr, beta1, beta2, adam_eps, tau, lamda, nullptr, -1, C, K, D, stream);
+}
+
 extern "C" int mgp_em_estep(const float* x, const float* mu, const float* sigma, const float* pi, float* log_resp,
                             float* score, int n, int K, int D, void* stream) {
     if (!x || !mu || !sigma || !pi || n <= 0 || K <= 0 || D <= 0) return MGP_ERR_INVALID;

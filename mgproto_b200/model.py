@@ -111,7 +111,9 @@ class MGProto(nn.Module):
         self.math_mode = "auto"          # 'fp32' exact SIMT | 'tc' tcgen05 fp16x3 | 'auto'
         self.em_n_split = 2              # row splits of the EM statistics reduction
         self.em_group = None             # torch.distributed process group for the sharded EM (parallel.py)
-        self._em_pending = None          # (pinned n_active, event) of the last update_GMM
+        self._adam_step_dev = None       # int32[1] on the device: Adam step count, advanced by update_GMM's planner
+        self._adam_step_seen = None      # host value the device counter was seeded from / last folded back to
+        self._em_dirty = False           # device counter ahead of prototype_optimizer.state[...]['step']
 
     # -- reference attribute: CPU bool flags ----------------------------------------------------
     @property
@@ -202,15 +204,18 @@ class MGProto(nn.Module):
         return g
 
     def sync_optimizer_state(self):
-        """Fold the (asynchronously read back) number of Adam steps of the last update_GMM into
-        ``prototype_optimizer.state[...]['step']``.  Called lazily; call it before inspecting or
-        saving the optimiser."""
-        if self._em_pending is not None:
-            host, ev, steps_per = self._em_pending
-            ev.synchronize()
+        """Fold the Adam step count kept on the device (advanced by every update_GMM without touching the host)
+        into ``prototype_optimizer.state[...]['step']``.  Synchronises; call it before inspecting or saving the
+        optimiser.  update_GMM itself never waits for the device."""
+        if self._em_dirty:
+            v = int(self._adam_step_dev.item())
             st = self.prototype_optimizer.state[self.prototype_means]
-            st["step"] += float(int(host[0]) * steps_per)
-            self._em_pending = None
+            if torch.is_tensor(st["step"]):
+                st["step"].fill_(float(v))
+            else:
+                st["step"] = v
+            self._adam_step_seen = v
+            self._em_dirty = False
 
     def _adam_state(self):
         opt, p = self.prototype_optimizer, self.prototype_means
@@ -250,11 +255,23 @@ class MGProto(nn.Module):
         if group is None:
             return self._update_GMM_generic(order, sched, stats, n_split, r0, r1, world)
 
-        self.sync_optimizer_state()
         st = self._adam_state()
-        step0 = int(st["step"])
+        host_step = int(st["step"])
+        if self._adam_step_dev is None or self._adam_step_dev.device != dev or host_step != self._adam_step_seen:
+            # first call, or the optimiser state was replaced / stepped elsewhere: (re)seed the device counter
+            if self._em_dirty and self._adam_step_dev is not None:
+                host_step += int(self._adam_step_dev.item()) - self._adam_step_seen   # keep the steps not folded back yet
+                st["step"] = torch.tensor(float(host_step)) if torch.is_tensor(st["step"]) else host_step
+            self._adam_step_dev = torch.tensor([host_step], dtype=torch.int32, device=dev)
+            self._adam_step_seen = host_step
+            self._em_dirty = False
         lr, (b1, b2), eps = group["lr"], group["betas"], group["eps"]
-        ops.em_plan(q.updated, q.mem_len, order, sched, step0, cap, L)
+        if world == 1:
+            ops.update_gmm(q.bank, q.updated, q.mem_len, mu, sg, wt, st["exp_avg"], st["exp_avg_sq"], self._adam_step_dev,
+                           order, sched, stats, n_split, L, self.alpha, lr, b1, b2, eps, self.tau)
+            self._em_dirty = True
+            return
+        ops.em_plan(q.updated, q.mem_len, order, sched, 0, cap, L, adam_step=self._adam_step_dev)
         ops.em_update(None, n_split, cap, order, sched, mu, sg, wt, st["exp_avg"], st["exp_avg_sq"], 0, L, 0,
                       lr, b1, b2, eps, self.tau)
         for i in range(L):
@@ -269,11 +286,7 @@ class MGProto(nn.Module):
                           lr, b1, b2, eps, self.tau)
         ops.em_update(None, n_split, cap, order, sched, mu, sg, wt, st["exp_avg"], st["exp_avg_sq"], 0, L, 2,
                       lr, b1, b2, eps, self.tau)
-        host = torch.empty(1, dtype=torch.int32, pin_memory=True)
-        host.copy_(sched[:1], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self._em_pending = (host, ev, L)
+        self._em_dirty = True
 
     def _update_GMM_generic(self, order, sched, stats, n_split, r0, r1, world):
         """Any other optimiser: same order of operations as the reference, one optimiser.step()

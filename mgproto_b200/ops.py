@@ -13,7 +13,7 @@ from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, M
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP, check)
 
 __all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
-           "bank_linearize", "em_plan", "em_stats", "em_update", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
+           "bank_linearize", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
 MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE,
@@ -333,6 +333,19 @@ def em_update(stats, n_split, n_rows_total, order, sched, mu_ckd, sigma_ckd, wei
                                     float(beta1), float(beta2), float(adam_eps), float(tau), float(lamda),
                                     _p(grad_out), int(only_class), C, K, D, _stream()), "mgp_em_update")
     _count(1)
+
+
+def update_gmm(bank, updated, mem_len, mu_ckd, sigma_ckd, weight_cp, exp_avg, exp_avg_sq, adam_step, order, sched, stats,
+               n_split, num_em_loop, alpha, lr, beta1, beta2, adam_eps, tau, lamda=1.0):
+    """ref model.py:277-301, single replica: plan + zero-gradient replays + num_em_loop x (stats, step) in one call."""
+    C, cap, D = bank.shape
+    K = mu_ckd.shape[1]
+    check(_lib.load().mgp_update_gmm(bank.data_ptr(), updated.data_ptr(), mem_len.data_ptr(), mu_ckd.data_ptr(),
+                                     sigma_ckd.data_ptr(), weight_cp.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                     adam_step.data_ptr(), order.data_ptr(), sched.data_ptr(), stats.data_ptr(),
+                                     int(n_split), int(num_em_loop), float(alpha), float(lr), float(beta1), float(beta2),
+                                     float(adam_eps), float(tau), float(lamda), C, K, D, cap, _stream()), "mgp_update_gmm")
+    _count(3 + 2 * int(num_em_loop))
 
 
 def em_estep(x_nd, mu_kd, sigma_kd, pi_k, want_log_resp=True, want_score=True):

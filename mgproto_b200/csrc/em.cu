@@ -17,6 +17,8 @@
 // (class, loop) step also decays the momentum of -- and moves -- all other classes.
 // Classes only interact through the global step count, so each class replays its own timeline.
 #include "mgp_common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -634,6 +636,372 @@ __device__ __forceinline__ void adam_apply(float& p, float& m, float& v, float g
     p = p - step_size * (m / denom);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The whole update_GMM of a single replica in ONE launch (after em_plan): classes only interact through the global
+// Adam step count (file header), so a cluster of two CTAs owns a class for all of its timeline --
+//   leading zero-gradient steps, num_em_loop x [E-step + statistics over the class's bank rows (each CTA half of
+//   them, partial sums exchanged through distributed shared memory), gradient + diversity + Adam step + pi
+//   momentum], trailing zero-gradient steps --
+// with the class's means, Adam moments and mixture weights held on chip in between.  Both CTAs carry identical
+// copies of that state (the exchange sums the two partials in rank order), rank 0 writes it back.  Arithmetic and
+// summation order are those of em_stats_fast_kernel (n_split = 2) + em_update_kernel.
+template <int D, int KH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 3)
+em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ order, const int32_t* __restrict__ sched,
+                float* __restrict__ mu, const float* __restrict__ sigma, float* __restrict__ weight,
+                float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float alpha, int rbf, int num_em_loop,
+                AdamCfg adam, float tau, float lamda, int C, int K, int cap) {
+    constexpr int DP = D + 4, K2 = 2 * KH, RS = (K2 + 3) & ~3, G = 256 / D, D4 = D / 4, TAB = 256;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = blockIdx.x >> 1, rank = blockIdx.x & 1;
+    const int ord = order[c];
+    const int n_active = sched[0], step0 = sched[1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = C * K, KD = K * D, L = num_em_loop;
+    extern __shared__ __align__(16) float sm[];
+    const int xfl = max(rbf * DP, (K + KD + 3 + G * K2 * D + 3) & ~3);
+    float* s_a = sm;                     // [K2][DP]  iso: -2 w_k mu_k, else mu_k (rows >= K zero)
+    float* s_ri = s_a + K2 * DP;         // [K2][DP]  1/(sigma+eps)
+    float* s_x = s_ri + K2 * DP;         // [rbf][DP] bank rows; afterwards group combine and the partials [K + KD]
+    float* s_r = s_x + xfl;              // [rbf][RS]
+    float* s_mu = s_r + rbf * RS;        // [K][D]    current means
+    float* s_cst = s_mu + K2 * D;        // [K2]
+    float* s_w = s_cst + K2;             // [K2]
+    float* s_ls = s_w + K2;              // [K2]      sum_d log(sigma + eps)
+    float* s_pi = s_ls + K2;             // [K2]
+    float* s_s0 = s_pi + K2;             // [K2]      S0 of the whole class
+    float* s_red = s_s0 + K2;            // [8][K2]
+    float* s_e = s_red + 8 * K2;         // [K][K]
+    float* s_c = s_e + K2 * K2;          // [TAB]
+    float* s_d = s_c + TAB;              // [TAB]
+    float* mu_c = mu + (size_t)c * KD;
+    const float* sg_c = sigma + (size_t)c * KD;
+
+    float p_[8], m_[8], v_[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int o = tid + 256 * i;
+        p_[i] = 0.f; m_[i] = 0.f; v_[i] = 1.f;
+        if (o < KD) {
+            p_[i] = mu_c[o];
+            m_[i] = exp_avg[(size_t)c * KD + o];
+            v_[i] = exp_avg_sq[(size_t)c * KD + o];
+        }
+    }
+    // `count` zero-gradient Adam steps first+1 .. first+count on the registers (see em_update_kernel phase 0/2)
+    auto replay = [&](int first, int count) {
+        if (count <= 0) return;
+        float a_[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a_[i] = sqrtf(v_[i]);
+        int cutoff = count;
+        if (adam.beta1 > 0.f && adam.beta1 < 1.f) cutoff = (int)ceilf(logf(1e-6f) / logf(adam.beta1));
+        const int count_p = min(count, max(cutoff, 1));
+        for (int s0 = 0; s0 < count_p; s0 += TAB) {
+            const int ns = min(TAB, count_p - s0);
+            __syncthreads();
+            for (int s = tid; s < ns; s += 256) {
+                const double st = (double)(s0 + s + 1);
+                const double l1 = log((double)adam.beta1), l2 = log((double)adam.beta2);
+                const double b1s = exp(st * l1), b2s = exp(st * l2);
+                const double b1t = exp(((double)first + st) * l1);
+                const double b2t = exp(((double)first + st) * l2);
+                s_c[s] = (float)((double)adam.lr * b1s / (1.0 - b1t));
+                s_d[s] = (float)(sqrt(b2s) / sqrt(1.0 - b2t));
+            }
+            __syncthreads();
+            for (int s = 0; s < ns; ++s) {
+                const float cs = -s_c[s], ds = s_d[s];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float rc;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.eps)));
+                    p_[i] = fmaf(cs * m_[i], rc, p_[i]);
+                }
+            }
+        }
+        const float mdec = (float)pow((double)adam.beta1, (double)count);
+        const float vdec = (float)pow((double)adam.beta2, (double)count);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { m_[i] *= mdec; v_[i] *= vdec; }
+    };
+    auto write_back = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = tid + 256 * i;
+            if (o < KD) {
+                mu_c[o] = p_[i];
+                exp_avg[(size_t)c * KD + o] = m_[i];
+                exp_avg_sq[(size_t)c * KD + o] = v_[i];
+            }
+        }
+    };
+
+    if (ord < 0) {                                   // inactive class: it only takes everybody's zero-gradient steps
+        if (rank == 0) {
+            replay(step0, L * n_active);
+            write_back();
+        }
+        return;
+    }
+    replay(step0, L * ord);
+
+    // sigma-derived constants (sigma does not change)
+    bool same = true;
+    for (int i = tid; i < KD; i += 256) same = same && (sg_c[i] == sg_c[(i / D) * D]);
+    const bool iso = __syncthreads_and(same ? 1 : 0) != 0;
+    for (int i = tid; i < K2 * D; i += 256) {
+        const int k = i / D, d = i - k * D;
+        s_ri[k * DP + d] = (k < K) ? 1.0f / (sg_c[i] + EM_EPS) : 0.f;                  // ref :333
+    }
+    for (int k = warp; k < K2; k += 8) {
+        float ls = 0.f;
+        if (k < K)
+            for (int d = lane; d < D; d += 32) ls += logf(sg_c[k * D + d] + EM_EPS);  // ref :334
+        ls = warp_sum(ls);
+        if (lane == 0) {
+            const float r0 = (k < K) ? 1.0f / (sg_c[k * D] + EM_EPS) : 0.f;
+            s_ls[k] = ls;
+            s_w[k] = r0 * r0;
+            s_pi[k] = (k < K) ? weight[(size_t)c * P + c * K + k] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int o = tid + 256 * i;
+        if (o < KD) s_mu[o] = p_[i];
+    }
+    __syncthreads();
+
+    const int per = (cap + 1) / 2;
+    const int seg_b = rank * per, seg_e = min(cap, seg_b + per);
+    const int row = tid >> 1, half = tid & 1;
+    const int pd = tid & (D - 1), pg = tid / D;
+    const float inv_den = 1.0f / (1.0f + (float)K * alpha);
+    const unsigned sx_addr = (unsigned)__cvta_generic_to_shared(s_x);
+    const float n_rows = (float)cap;
+    const float div_scale = -4.0f * lamda / ((float)K * (float)(K - 1));
+
+    for (int loop = 0; loop < L; ++loop) {
+        // packed means and per-component constants from the current state
+        for (int i = tid; i < K2 * D; i += 256) {
+            const int k = i / D, d = i - k * D;
+            float av = 0.f;
+            if (k < K) {
+                const float rv = s_ri[k * DP + d];
+                av = iso ? -2.0f * rv * rv * s_mu[i] : s_mu[i];
+            }
+            s_a[k * DP + d] = av;
+        }
+        for (int k = warp; k < K2; k += 8) {
+            float mm = 0.f;
+            if (k < K)
+                for (int d = lane; d < D; d += 32) mm = fmaf(s_mu[k * D + d], s_mu[k * D + d], mm);
+            mm = warp_sum(mm);
+            if (lane == 0)
+                s_cst[k] = (k < K) ? -0.5f * (float)D * MGP_LOG_2PI - s_ls[k] + logf(s_pi[k] + EM_EPS) -
+                                         (iso ? 0.5f * s_w[k] * mm : 0.f)
+                                   : 0.f;
+        }
+        __syncthreads();
+
+        float a1[K2], s0[KH];
+#pragma unroll
+        for (int i = 0; i < K2; ++i) a1[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < KH; ++i) s0[i] = 0.f;
+        for (int r0 = seg_b; r0 < seg_e; r0 += rbf) {
+            const int nr = min(rbf, seg_e - r0);
+            const float* src = bank + ((size_t)c * cap + r0) * D;
+            for (int q = tid; q < nr * D4; q += 256) {
+                const int rr = q / D4, c4 = q - rr * D4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx_addr + (unsigned)(rr * DP + 4 * c4) * 4u),
+                             "l"(src + (size_t)q * 4)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (warp * 16 < nr) {
+                const float* xr = s_x + min(row, nr - 1) * DP;
+                const float* ar = s_a + half * KH * DP;
+                const float* rr_ = s_ri + half * KH * DP;
+                float acc[KH], xx = 0.f;
+#pragma unroll
+                for (int i = 0; i < KH; ++i) acc[i] = 0.f;
+                if (iso) {
+#pragma unroll 4
+                    for (int j = 0; j < D4; ++j) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
+                        xx = fmaf(xv.x, xv.x, xx); xx = fmaf(xv.y, xv.y, xx);
+                        xx = fmaf(xv.z, xv.z, xx); xx = fmaf(xv.w, xv.w, xx);
+#pragma unroll
+                        for (int i = 0; i < KH; ++i) {
+                            const float4 m = *reinterpret_cast<const float4*>(ar + i * DP + 4 * j);
+                            acc[i] = fmaf(xv.x, m.x, acc[i]); acc[i] = fmaf(xv.y, m.y, acc[i]);
+                            acc[i] = fmaf(xv.z, m.z, acc[i]); acc[i] = fmaf(xv.w, m.w, acc[i]);
+                        }
+                    }
+                } else {
+#pragma unroll 2
+                    for (int j = 0; j < D4; ++j) {
+                        const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
+#pragma unroll
+                        for (int i = 0; i < KH; ++i) {
+                            const float4 m = *reinterpret_cast<const float4*>(ar + i * DP + 4 * j);
+                            const float4 ri = *reinterpret_cast<const float4*>(rr_ + i * DP + 4 * j);
+                            float t;
+                            t = (xv.x - m.x) * ri.x; acc[i] = fmaf(t, t, acc[i]);
+                            t = (xv.y - m.y) * ri.y; acc[i] = fmaf(t, t, acc[i]);
+                            t = (xv.z - m.z) * ri.z; acc[i] = fmaf(t, t, acc[i]);
+                            t = (xv.w - m.w) * ri.w; acc[i] = fmaf(t, t, acc[i]);
+                        }
+                    }
+                }
+                float wl[KH], mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < KH; ++i) {
+                    const int k = half * KH + i;
+                    const float q = iso ? fmaf(s_w[k], xx, acc[i]) : acc[i];
+                    wl[i] = (k < K) ? s_cst[k] - 0.5f * q : -INFINITY;                // ref :316
+                    mx = fmaxf(mx, wl[i]);
+                }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                float se = 0.f;
+#pragma unroll
+                for (int i = 0; i < KH; ++i) {
+                    wl[i] = (half * KH + i < K) ? expf(wl[i] - mx) : 0.f;
+                    se += wl[i];
+                }
+                se += __shfl_xor_sync(0xffffffffu, se, 1);
+                const float inv_se = 1.0f / se;
+                const bool live = row < nr;
+#pragma unroll
+                for (int i = 0; i < KH; ++i) {
+                    const int k = half * KH + i;
+                    const float r = (k < K && live) ? fmaf(wl[i], inv_se, alpha) * inv_den : 0.f;   // ref :380-383
+                    s0[i] += r;
+                    if (live) s_r[row * RS + k] = r;
+                }
+            }
+            __syncthreads();
+            {
+                const int per_g = (nr + G - 1) / G;
+                const int rb = pg * per_g, re = min(nr, rb + per_g);
+#pragma unroll 2
+                for (int rl = rb; rl < re; ++rl) {
+                    const float xv = s_x[rl * DP + pd];
+                    float rv[RS];
+#pragma unroll
+                    for (int i = 0; i < RS / 4; ++i)
+                        *reinterpret_cast<float4*>(rv + 4 * i) = *reinterpret_cast<const float4*>(s_r + rl * RS + 4 * i);
+#pragma unroll
+                    for (int i = 0; i < K2; ++i) a1[i] = fmaf(rv[i], xv, a1[i]);
+                }
+            }
+            __syncthreads();
+        }
+        // this CTA's partial sums -> s_x: [0,K) S0, [K, K+KD) S1 (group combine staged behind them)
+#pragma unroll
+        for (int i = 0; i < KH; ++i) {
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
+            if (lane < 2) s_red[warp * K2 + lane * KH + i] = s0[i];
+        }
+        float part1[8];
+        // group combine: each group writes its a1 to its own slice, then owners sum the slices
+        float* gsl = s_x + ((K + KD + 3) & ~3);                   // [G][K2][D]
+#pragma unroll
+        for (int i = 0; i < K2; ++i) gsl[(pg * K2 + i) * D + pd] = a1[i];
+        __syncthreads();
+        if (tid < K) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += s_red[w * K2 + tid];
+            s_x[tid] = t;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = tid + 256 * i;
+            part1[i] = 0.f;
+            if (o < KD) {
+                const int k = o / D, d = o - k * D;
+                float t = 0.f;
+#pragma unroll
+                for (int g = 0; g < G; ++g) t += gsl[(g * K2 + k) * D + d];
+                part1[i] = t;
+                s_x[K + o] = t;
+            }
+        }
+        cluster.sync();                                           // both partials are published
+        const float* rem = cluster.map_shared_rank(s_x, rank ^ 1);
+        float s1_[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = tid + 256 * i;
+            s1_[i] = 0.f;
+            if (o < KD) {
+                const float other = rem[K + o];
+                s1_[i] = (rank == 0) ? part1[i] + other : other + part1[i];   // split 0 + split 1, as em_update_kernel sums them
+            }
+        }
+        if (tid < K) {
+            const float mine = s_x[tid], other = rem[tid];
+            s_s0[tid] = (rank == 0) ? mine + other : other + mine;
+        }
+        // diversity kernel on the current means (ref utils/helpers.py:13-14, model.py:390-392)
+        for (int pr = warp; pr < K * K; pr += 8) {
+            const int i = pr / K, j = pr - i * K;
+            float t = 0.f;
+            for (int d = lane; d < D; d += 32) {
+                const float df = s_mu[i * D + d] - s_mu[j * D + d];
+                t = fmaf(df, df, t);
+            }
+            t = warp_sum(t);
+            if (lane == 0) s_e[pr] = (i == j) ? 0.f : expf(-t);
+        }
+        cluster.sync();                                           // the partner has read my partials; s_s0 / s_e visible
+        const int step = step0 + L * ord + loop + 1;
+        const double b1p = pow((double)adam.beta1, (double)step), b2p = pow((double)adam.beta2, (double)step);
+        float newp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = tid + 256 * i;
+            newp[i] = p_[i];
+            if (o >= KD) continue;
+            const int k = o / D, d = o - k * D;
+            const float sg = sg_c[o] + EM_EPS;
+            const float w = 1.0f / (sg * sg);
+            const float muv = s_mu[o];
+            float g = -(s1_[i] - muv * s_s0[k]) * w / n_rows;
+            float esum = 0.f, emu = 0.f;
+            for (int j = 0; j < K; ++j) {
+                const float e = s_e[k * K + j];
+                esum += e;
+                emu = fmaf(e, s_mu[j * D + d], emu);
+            }
+            g += div_scale * (esum * muv - emu);
+            float pp = muv, mm = m_[i], vv = v_[i];
+            adam_apply(pp, mm, vv, g, adam, b1p, b2p);
+            newp[i] = pp; m_[i] = mm; v_[i] = vv;
+        }
+        __syncthreads();                                          // every reader of the old means is done
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = tid + 256 * i;
+            p_[i] = newp[i];
+            if (o < KD) s_mu[o] = newp[i];
+        }
+        if (tid < K) s_pi[tid] = tau * s_pi[tid] + (1.0f - tau) * ((s_s0[tid] + EM_EPS) / n_rows);   // ref :385, :399
+        __syncthreads();
+    }
+    replay(step0 + L * (ord + 1), L * (n_active - ord - 1));
+    if (rank == 0) {
+        write_back();
+        if (tid < K) weight[(size_t)c * P + (size_t)c * K + tid] = s_pi[tid];
+    }
+}
+
 // grid C, block 256.  See the file header for the phases.
 __global__ void __launch_bounds__(256)
 em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_stride, int n_rows_total,
@@ -1010,6 +1378,33 @@ extern "C" int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t
         return MGP_ERR_INVALID;
     int rc = mgp_em_plan(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop, stream);
     if (rc != MGP_OK) return rc;
+    static const bool unfused = (getenv("MGP_EM_UNFUSED") != nullptr);
+    if (!unfused && K >= 2 && K <= 16 && (D == 64 || D == 128) && cap >= 2) {
+        // one cluster of two CTAs per class runs the class's whole timeline (em_fused_kernel)
+        const int kh = (K + 1) / 2 <= 3 ? 3 : ((K + 1) / 2 <= 5 ? 5 : 8);
+        const int per = (cap + 1) / 2;
+        const int nb = (per + 87) / 88;
+        int rbf = (((per + nb - 1) / nb) + 3) & ~3;
+        if (rbf < 32) rbf = 32;
+        const int k2 = 2 * kh, rs = (k2 + 3) & ~3, g = 256 / D, dp = D + 4;
+        int xfl = (K + K * D + 3 + g * k2 * D + 3) & ~3;
+        if (rbf * dp > xfl) xfl = rbf * dp;
+        const size_t fsmem = ((size_t)2 * k2 * dp + xfl + (size_t)rbf * rs + (size_t)k2 * D + 13 * k2 + (size_t)k2 * k2 + 512) *
+                             sizeof(float);
+        AdamCfg a{lr, beta1, beta2, adam_eps};
+        cudaStream_t fst = (cudaStream_t)stream;
+#define MGP_EM_FUSED(DD, KK)                                                                                        \
+    if (D == DD && kh == KK) {                                                                                      \
+        MGP_CUDA(cudaFuncSetAttribute(em_fused_kernel<DD, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+        em_fused_kernel<DD, KK><<<2 * C, 256, fsmem, fst>>>(bank, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq, \
+                                                            alpha, rbf, num_em_loop, a, tau, lamda, C, K, cap);     \
+        MGP_CHECK_LAUNCH();                                                                                         \
+        return MGP_OK;                                                                                              \
+    }
+        MGP_EM_FUSED(128, 3) MGP_EM_FUSED(128, 5) MGP_EM_FUSED(128, 8)
+        MGP_EM_FUSED(64, 3) MGP_EM_FUSED(64, 5) MGP_EM_FUSED(64, 8)
+#undef MGP_EM_FUSED
+    }
     rc = mgp_em_update(nullptr, n_split, 0, cap, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq, 0, num_em_loop,
                        0, lr, beta1, beta2, adam_eps, tau, lamda, nullptr, -1, C, K, D, stream);
     if (rc != MGP_OK) return rc;

@@ -494,18 +494,26 @@ em_stats_fast_kernel(const float* __restrict__ bank, const int32_t* __restrict__
 #pragma unroll
             for (int i = 0; i < KH; ++i) acc[i] = 0.f;
             if (iso) {
+                // paired FMAs (FFMA2): even / odd dims accumulate separately and are added at the end
+                float2 acc2[KH], xx2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < KH; ++i) acc2[i] = make_float2(0.f, 0.f);
 #pragma unroll 4
                 for (int j = 0; j < D4; ++j) {
                     const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
-                    xx = fmaf(xv.x, xv.x, xx); xx = fmaf(xv.y, xv.y, xx);
-                    xx = fmaf(xv.z, xv.z, xx); xx = fmaf(xv.w, xv.w, xx);
+                    const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
+                    xx2 = ffma2(x01, x01, xx2);
+                    xx2 = ffma2(x23, x23, xx2);
 #pragma unroll
                     for (int i = 0; i < KH; ++i) {
                         const float4 m = *reinterpret_cast<const float4*>(ar + i * DP + 4 * j);
-                        acc[i] = fmaf(xv.x, m.x, acc[i]); acc[i] = fmaf(xv.y, m.y, acc[i]);
-                        acc[i] = fmaf(xv.z, m.z, acc[i]); acc[i] = fmaf(xv.w, m.w, acc[i]);
+                        acc2[i] = ffma2(x01, make_float2(m.x, m.y), acc2[i]);
+                        acc2[i] = ffma2(x23, make_float2(m.z, m.w), acc2[i]);
                     }
                 }
+                xx = xx2.x + xx2.y;
+#pragma unroll
+                for (int i = 0; i < KH; ++i) acc[i] = acc2[i].x + acc2[i].y;
             } else {
 #pragma unroll 2
                 for (int j = 0; j < D4; ++j) {
@@ -561,10 +569,16 @@ em_stats_fast_kernel(const float* __restrict__ bank, const int32_t* __restrict__
 #pragma unroll
                 for (int i = 0; i < RS / 4; ++i)
                     *reinterpret_cast<float4*>(rv + 4 * i) = *reinterpret_cast<const float4*>(s_r + rl * RS + 4 * i);
+                const float2 xd = make_float2(xv, xv);
 #pragma unroll
-                for (int i = 0; i < K2; ++i) {
-                    a1[i] = fmaf(rv[i], xv, a1[i]);
-                    if (WITH_S2) a2[i] = fmaf(rv[i] * xv, xv, a2[i]);
+                for (int q = 0; q < K2 / 2; ++q) {              // FFMA2: two components per issue slot
+                    const float2 t = ffma2(make_float2(rv[2 * q], rv[2 * q + 1]), xd, make_float2(a1[2 * q], a1[2 * q + 1]));
+                    a1[2 * q] = t.x;
+                    a1[2 * q + 1] = t.y;
+                }
+                if (WITH_S2) {
+#pragma unroll
+                    for (int i = 0; i < K2; ++i) a2[i] = fmaf(rv[i] * xv, xv, a2[i]);
                 }
             }
         }
@@ -652,6 +666,7 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
                 float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float alpha, int rbf, int num_em_loop,
                 AdamCfg adam, float tau, float lamda, int C, int K, int cap) {
     constexpr int DP = D + 4, K2 = 2 * KH, RS = (K2 + 3) & ~3, G = 256 / D, D4 = D / 4, TAB = 256;
+    constexpr int NE = (K2 * D + 255) / 256;                     // elements of the class's [K,D] state owned by a thread
     cg::cluster_group cluster = cg::this_cluster();
     const int c = blockIdx.x >> 1, rank = blockIdx.x & 1;
     const int ord = order[c];
@@ -674,12 +689,13 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
     float* s_e = s_red + 8 * K2;         // [K][K]
     float* s_c = s_e + K2 * K2;          // [TAB]
     float* s_d = s_c + TAB;              // [TAB]
+    __shared__ float s_adam[2];
     float* mu_c = mu + (size_t)c * KD;
     const float* sg_c = sigma + (size_t)c * KD;
 
-    float p_[8], m_[8], v_[8];
+    float p_[NE], m_[NE], v_[NE];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NE; ++i) {
         const int o = tid + 256 * i;
         p_[i] = 0.f; m_[i] = 0.f; v_[i] = 1.f;
         if (o < KD) {
@@ -691,9 +707,9 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
     // `count` zero-gradient Adam steps first+1 .. first+count on the registers (see em_update_kernel phase 0/2)
     auto replay = [&](int first, int count) {
         if (count <= 0) return;
-        float a_[8];
+        float a_[NE];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a_[i] = sqrtf(v_[i]);
+        for (int i = 0; i < NE; ++i) a_[i] = sqrtf(v_[i]);
         int cutoff = count;
         if (adam.beta1 > 0.f && adam.beta1 < 1.f) cutoff = (int)ceilf(logf(1e-6f) / logf(adam.beta1));
         const int count_p = min(count, max(cutoff, 1));
@@ -713,7 +729,7 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
             for (int s = 0; s < ns; ++s) {
                 const float cs = -s_c[s], ds = s_d[s];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < NE; ++i) {
                     float rc;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.eps)));
                     p_[i] = fmaf(cs * m_[i], rc, p_[i]);
@@ -723,11 +739,11 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
         const float mdec = (float)pow((double)adam.beta1, (double)count);
         const float vdec = (float)pow((double)adam.beta2, (double)count);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { m_[i] *= mdec; v_[i] *= vdec; }
+        for (int i = 0; i < NE; ++i) { m_[i] *= mdec; v_[i] *= vdec; }
     };
     auto write_back = [&]() {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NE; ++i) {
             const int o = tid + 256 * i;
             if (o < KD) {
                 mu_c[o] = p_[i];
@@ -767,7 +783,7 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NE; ++i) {
         const int o = tid + 256 * i;
         if (o < KD) s_mu[o] = p_[i];
     }
@@ -830,18 +846,26 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
 #pragma unroll
                 for (int i = 0; i < KH; ++i) acc[i] = 0.f;
                 if (iso) {
+                    // paired FMAs (FFMA2): even / odd dims accumulate separately and are added at the end
+                    float2 acc2[KH], xx2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < KH; ++i) acc2[i] = make_float2(0.f, 0.f);
 #pragma unroll 4
                     for (int j = 0; j < D4; ++j) {
                         const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
-                        xx = fmaf(xv.x, xv.x, xx); xx = fmaf(xv.y, xv.y, xx);
-                        xx = fmaf(xv.z, xv.z, xx); xx = fmaf(xv.w, xv.w, xx);
+                        const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
+                        xx2 = ffma2(x01, x01, xx2);
+                        xx2 = ffma2(x23, x23, xx2);
 #pragma unroll
                         for (int i = 0; i < KH; ++i) {
                             const float4 m = *reinterpret_cast<const float4*>(ar + i * DP + 4 * j);
-                            acc[i] = fmaf(xv.x, m.x, acc[i]); acc[i] = fmaf(xv.y, m.y, acc[i]);
-                            acc[i] = fmaf(xv.z, m.z, acc[i]); acc[i] = fmaf(xv.w, m.w, acc[i]);
+                            acc2[i] = ffma2(x01, make_float2(m.x, m.y), acc2[i]);
+                            acc2[i] = ffma2(x23, make_float2(m.z, m.w), acc2[i]);
                         }
                     }
+                    xx = xx2.x + xx2.y;
+#pragma unroll
+                    for (int i = 0; i < KH; ++i) acc[i] = acc2[i].x + acc2[i].y;
                 } else {
 #pragma unroll 2
                     for (int j = 0; j < D4; ++j) {
@@ -895,8 +919,13 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
 #pragma unroll
                     for (int i = 0; i < RS / 4; ++i)
                         *reinterpret_cast<float4*>(rv + 4 * i) = *reinterpret_cast<const float4*>(s_r + rl * RS + 4 * i);
+                    const float2 xd = make_float2(xv, xv);
 #pragma unroll
-                    for (int i = 0; i < K2; ++i) a1[i] = fmaf(rv[i], xv, a1[i]);
+                    for (int q = 0; q < K2 / 2; ++q) {          // FFMA2: two components per issue slot
+                        const float2 t = ffma2(make_float2(rv[2 * q], rv[2 * q + 1]), xd, make_float2(a1[2 * q], a1[2 * q + 1]));
+                        a1[2 * q] = t.x;
+                        a1[2 * q + 1] = t.y;
+                    }
                 }
             }
             __syncthreads();
@@ -908,7 +937,7 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
             for (int o = 2; o < 32; o <<= 1) s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
             if (lane < 2) s_red[warp * K2 + lane * KH + i] = s0[i];
         }
-        float part1[8];
+        float part1[NE];
         // group combine: each group writes its a1 to its own slice, then owners sum the slices
         float* gsl = s_x + ((K + KD + 3) & ~3);                   // [G][K2][D]
 #pragma unroll
@@ -921,7 +950,7 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
             s_x[tid] = t;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NE; ++i) {
             const int o = tid + 256 * i;
             part1[i] = 0.f;
             if (o < KD) {
@@ -935,9 +964,9 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
         }
         cluster.sync();                                           // both partials are published
         const float* rem = cluster.map_shared_rank(s_x, rank ^ 1);
-        float s1_[8];
+        float s1_[NE];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NE; ++i) {
             const int o = tid + 256 * i;
             s1_[i] = 0.f;
             if (o < KD) {
@@ -960,12 +989,17 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
             t = warp_sum(t);
             if (lane == 0) s_e[pr] = (i == j) ? 0.f : expf(-t);
         }
-        cluster.sync();                                           // the partner has read my partials; s_s0 / s_e visible
-        const int step = step0 + L * ord + loop + 1;
-        const double b1p = pow((double)adam.beta1, (double)step), b2p = pow((double)adam.beta2, (double)step);
-        float newp[8];
+        if (tid == 0) {
+            const double stp = (double)(step0 + L * ord + loop + 1);
+            s_adam[0] = (float)((double)adam.lr / (1.0 - pow((double)adam.beta1, stp)));
+            s_adam[1] = (float)sqrt(1.0 - pow((double)adam.beta2, stp));
+        }
+        cluster.sync();                                           // the partner has read my partials; s_s0 / s_e / s_adam visible
+        // Adam's bias corrections of this step (torch: double), computed once per CTA
+        const float step_size = s_adam[0], bc2_sqrt = s_adam[1];
+        float newp[NE];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NE; ++i) {
             const int o = tid + 256 * i;
             newp[i] = p_[i];
             if (o >= KD) continue;
@@ -981,13 +1015,16 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
                 emu = fmaf(e, s_mu[j * D + d], emu);
             }
             g += div_scale * (esum * muv - emu);
-            float pp = muv, mm = m_[i], vv = v_[i];
-            adam_apply(pp, mm, vv, g, adam, b1p, b2p);
-            newp[i] = pp; m_[i] = mm; v_[i] = vv;
+            // torch.optim.Adam (_single_tensor_adam): lerp, mul/addcmul
+            const float mm = m_[i] + (g - m_[i]) * (1.0f - adam.beta1);
+            const float vv = v_[i] * adam.beta2 + (1.0f - adam.beta2) * g * g;
+            const float denom = sqrtf(vv) / bc2_sqrt + adam.eps;
+            newp[i] = muv - step_size * (mm / denom);
+            m_[i] = mm; v_[i] = vv;
         }
         __syncthreads();                                          // every reader of the old means is done
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NE; ++i) {
             const int o = tid + 256 * i;
             p_[i] = newp[i];
             if (o < KD) s_mu[o] = newp[i];

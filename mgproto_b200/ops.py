@@ -230,10 +230,13 @@ class HeadFunction(torch.autograd.Function):
         ctx.has_gt = gt is not None
         ctx.dims = (B, HW, C, K, D, T, H, W)
         ctx.mark_non_differentiable(xhat, idx)
+        ctx.set_materialize_grads(False)      # no zero-filled "gradients" for xhat [N,D] / idx [B,P,T] (67 MB of fills)
         return logits, xhat, idx
 
     @staticmethod
     def backward(ctx, g_logits, _g_xhat, _g_idx):
+        if g_logits is None:
+            return (None,) * 7
         logits, vals, idx, wt, gt, xhat, inv, mu, sg = ctx.saved_tensors
         B, HW, C, K, D, T, H, W = ctx.dims
         g = _req(g_logits.contiguous(), torch.float32, "grad_logits")

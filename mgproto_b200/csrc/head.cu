@@ -284,27 +284,37 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
         }
         __syncthreads();
         // log p[n,k] = -D/2 log 2pi - sum log sigma - 1/2 sum ((x-mu)/sigma)^2   (ref model.py:256-275, exact form)
-        for (int n = threadIdx.x; n < HW; n += 256) {
+        // thread = (patch n, half of the prototypes): eight 16-byte loads of the patch row are in flight at a time
+        // (the row is read once; prototype rows are shared-memory broadcasts)
+        const int KHh = (K + 1) / 2;
+        for (int it = threadIdx.x; it < 2 * HW; it += 256) {
+            const int n = it >> 1, kb = (it & 1) * KHh, ke = min(K, kb + KHh);
             const float4* xr = reinterpret_cast<const float4*>(xhat + ((size_t)b * HW + n) * D);
-            for (int k0 = 0; k0 < K; k0 += 5) {
+            for (int k0 = kb; k0 < ke; k0 += 5) {
                 float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int d4 = 0; d4 < D / 4; ++d4) {
-                    const float4 xv = __ldg(xr + d4);
+                for (int d0 = 0; d0 < D / 4; d0 += 8) {
+                    float4 xv[8];
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const int k = min(k0 + i, K - 1);
-                        const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + 4 * d4);
-                        const float4 r = *reinterpret_cast<const float4*>(s_ri + k * D + 4 * d4);
-                        float t;
-                        t = (xv.x - m.x) * r.x; q[i] = fmaf(t, t, q[i]);
-                        t = (xv.y - m.y) * r.y; q[i] = fmaf(t, t, q[i]);
-                        t = (xv.z - m.z) * r.z; q[i] = fmaf(t, t, q[i]);
-                        t = (xv.w - m.w) * r.w; q[i] = fmaf(t, t, q[i]);
+                    for (int u = 0; u < 8; ++u) xv[u] = (d0 + u < D / 4) ? __ldg(xr + d0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (d0 + u >= D / 4) break;
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const int k = min(k0 + i, K - 1);
+                            const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + 4 * (d0 + u));
+                            const float4 r = *reinterpret_cast<const float4*>(s_ri + k * D + 4 * (d0 + u));
+                            float t;
+                            t = (xv[u].x - m.x) * r.x; q[i] = fmaf(t, t, q[i]);
+                            t = (xv[u].y - m.y) * r.y; q[i] = fmaf(t, t, q[i]);
+                            t = (xv[u].z - m.z) * r.z; q[i] = fmaf(t, t, q[i]);
+                            t = (xv[u].w - m.w) * r.w; q[i] = fmaf(t, t, q[i]);
+                        }
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < 5; ++i)
-                    if (k0 + i < K) lp[(k0 + i) * HWp + n] = -0.5f * (float)D * MGP_LOG_2PI - s_ls[k0 + i] - 0.5f * q[i];
+                    if (k0 + i < ke) lp[(k0 + i) * HWp + n] = -0.5f * (float)D * MGP_LOG_2PI - s_ls[k0 + i] - 0.5f * q[i];
             }
         }
         __syncthreads();

@@ -373,33 +373,32 @@ __global__ void proto_weight_kernel(const float* __restrict__ mu, const float* _
 
 constexpr int LCAP = 2304;   // entries per drain (>= P + K(T-1) of the labelled cfg: one drain per image)
 
-// grid (B, D/DC), DC = 64: CTA (b, j) builds dims [64j, 64j+64) of image b's gradient tile G[HW][DC] in shared
-// memory.  Entries with gradient are compacted in a fixed order, stably counting-sorted by patch row, then each
-// warp walks one eighth of the sorted list with lanes owning two dims each (see the walk below): balanced
-// however the mined patches cluster, no atomics, fixed summation order.
-__global__ void __launch_bounds__(256, 2)
+// grid (B, D/DC), DC = 64: CTA (b, j) produces dims [64j, 64j+64) of image b's rows of g_xhat (zeroed by the
+// caller).  Entries with gradient are compacted in a fixed order, stably counting-sorted by patch row, then each
+// warp walks one eighth of the sorted list with lanes owning two dims each (see the walk below) and adds every
+// finished row straight into global memory (a row has exactly one writer per drain): balanced however the mined
+// patches cluster, no atomics, fixed summation order, 48 KB of shared memory -> 4 CTAs per SM.
+__global__ void __launch_bounds__(256, 4)
 head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, const float* __restrict__ vals,
                 const int32_t* __restrict__ idx, const float* __restrict__ weight, const int64_t* __restrict__ gt,
                 const float* __restrict__ xhat, const float* __restrict__ w, const float* __restrict__ wm,
                 const float* __restrict__ wsc, const int* __restrict__ noniso, float* __restrict__ g_xhat, int HW,
                 int C, int K, int D, int T, int DC) {
     extern __shared__ float smem[];
-    const int pitch = DC;                                   // even: rows are float2-addressable
     const bool aniso = (*noniso != 0);
-    float* G = smem;                                        // [HW][pitch]
-    unsigned* lkey = reinterpret_cast<unsigned*>(G + (size_t)HW * pitch);     // [LCAP] p*1024 + n
+    unsigned* lkey = reinterpret_cast<unsigned*>(smem);     // [LCAP] p*1024 + n
     float* lval = reinterpret_cast<float*>(lkey + LCAP);    // [LCAP]
     unsigned* skey = reinterpret_cast<unsigned*>(lval + LCAP);                // [LCAP] sorted by row
     float* sval = reinterpret_cast<float*>(skey + LCAP);    // [LCAP]
     int* bins = reinterpret_cast<int*>(sval + LCAP);        // [8][HW] per-warp row histograms / start offsets
-    float* g2 = reinterpret_cast<float*>(bins + 8 * HW);    // [HW] sum_e a_e * w_p per row (isotropic sigma)
-    float* Qs = g2 + HW;                                    // [C]  sum_t gl/exp(logit)      (wrong-class fold)
+    float* Qs = reinterpret_cast<float*>(bins + 8 * HW);    // [C]  sum_t gl/exp(logit)      (wrong-class fold)
     float* qg = Qs + C;                                     // [T]  gl/exp(logit) of the GT class
     __shared__ int wcount[8];
     __shared__ int lcount;
-    __shared__ __align__(8) float part[16 * 64];            // boundary runs of the warps' list ranges
-    __shared__ float part2[16];
+    __shared__ __align__(8) float part[16 * 64];            // boundary runs of the warps' list ranges (s1 vectors)
+    __shared__ float part2[16];                             // ... their scalar sum_e a_e w_p (isotropic sigma)
     __shared__ int prow[16];
+    __shared__ int mrow[16], mcount;                        // boundary runs merged by row
 
     const int b = blockIdx.x;
     const int d0 = blockIdx.y * DC;
@@ -409,8 +408,6 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     const bool has_gt = (gt != nullptr);
     const long long g = has_gt ? (long long)gt[b] : -1;
 
-    for (int i = threadIdx.x; i < HW * pitch; i += 256) G[i] = 0.f;
-    for (int i = threadIdx.x; i < HW; i += 256) g2[i] = 0.f;
     if (has_gt) {
         if (C * T <= 2 * LCAP) {
             // q[c][t] = gl / exp(logit) for the whole image in one coalesced pass (staged in the sorted-list
@@ -564,56 +561,47 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
             __syncthreads();
             // Walk: warp w owns the w-th eighth of the row-sorted list (balanced however the patches cluster),
             // lanes own two dims each, so one instruction handles one entry x 64 dims and the prototype rows
-            // are read as coalesced 256-byte segments, eight in flight.  Per row:
-            //   G[n] += sum_e a_e * wm_p  -  xhat_n * sum_e a_e * w_p
-            // (w_p is a per-prototype scalar when every sigma is isotropic: then the second sum is the scalar
-            // g2[n], applied at copy-out).  Runs inside a warp's range are complete rows (single writer);
-            // the first and last run of a range may continue in the neighbour's range: they are parked in
-            // `part` and folded in by one warp in a fixed order -> no atomics, deterministic.
+            // are read as coalesced 256-byte segments, eight in flight.  Per row n:
+            //   g[n] += sum_e a_e * wm_p  -  xhat_n * sum_e a_e * w_p
+            // (w_p is a per-prototype scalar when every sigma is isotropic).  xhat_n and the old g[n] are fetched
+            // when a run starts and used when it ends.  Runs inside a warp's range are complete rows (single
+            // writer); the first and last run of a range may continue in the neighbour's range: they are parked in
+            // `part`, merged by row in a fixed order and added afterwards -> no atomics, deterministic.
             if (threadIdx.x < 16) prow[threadIdx.x] = -1;
             __syncthreads();
+            const int dl = 2 * lane;
+            const bool dok2 = dl < dc;
+            const int dle = dok2 ? dl : 0;                       // lanes beyond dc shadow the first dims, never store
+            const float* xcol2 = xhat + (size_t)b * HW * D + d0 + dle;
+            float* gcol = g_xhat + (size_t)b * HW * D + d0 + dle;
             {
                 const int wseg = (cnt + 7) / 8, wb = min(cnt, warp * wseg), we = min(cnt, wb + wseg);
-                const int dl = 2 * lane;
-                const bool dok2 = dl < dc;
-                const float* wmcol = wm + d0 + dl;
-                const float* wcol = w + d0 + dl;
-                const float* xcol2 = xhat + (size_t)b * HW * D + d0 + dl;
+                const float* wmcol_l = wm + d0 + dle;
+                const float* wcol_l = w + d0 + dle;
                 int cur_n = -1;
                 bool first_run = true;
                 float2 s1 = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
+                float2 xpre = make_float2(0.f, 0.f), gpre = make_float2(0.f, 0.f);
                 float s2 = 0.f;
                 auto flush = [&](int slot) {
-                    float2 v = s1;
-                    if (aniso && dok2) {
-                        const float2 xv = __ldg(reinterpret_cast<const float2*>(xcol2 + (size_t)cur_n * D));
-                        v.x = fmaf(-xv.x, s2v.x, v.x);
-                        v.y = fmaf(-xv.y, s2v.y, v.y);
-                    }
                     if (slot < 0) {
-                        if (dok2) {
-                            float2* gp = reinterpret_cast<float2*>(G + (size_t)cur_n * pitch + dl);
-                            float2 t = *gp;
-                            t.x += v.x;
-                            t.y += v.y;
-                            *gp = t;
-                        }
-                        if (lane == 0) g2[cur_n] += s2;
+                        float2 v = gpre;
+                        v.x += aniso ? fmaf(-xpre.x, s2v.x, s1.x) : fmaf(-xpre.x, s2, s1.x);
+                        v.y += aniso ? fmaf(-xpre.y, s2v.y, s1.y) : fmaf(-xpre.y, s2, s1.y);
+                        if (dok2) *reinterpret_cast<float2*>(gcol + (size_t)cur_n * D) = v;
                     } else {
+                        float2 v = s1;                            // isotropic: raw sums, xhat applied after the merge
+                        if (aniso) { v.x = fmaf(-xpre.x, s2v.x, v.x); v.y = fmaf(-xpre.y, s2v.y, v.y); }
                         if (dok2) *reinterpret_cast<float2*>(part + (warp * 2 + slot) * 64 + dl) = v;
-                        if (lane == 0) { part2[warp * 2 + slot] = s2; prow[warp * 2 + slot] = cur_n; }
+                        if (lane == 0) { part2[warp * 2 + slot] = aniso ? 0.f : s2; prow[warp * 2 + slot] = cur_n; }
                     }
                 };
-                // lanes beyond dc read (and discard) the CTA's first dims; list slots beyond the range repeat the
-                // range's last entry with a zero coefficient -> unconditional loads, no per-entry predicates
-                const float* wmcol_l = dok2 ? wmcol : wm + d0;
-                const float* wcol_l = dok2 ? wcol : w + d0;
                 auto walk = [&](auto aniso_tag) {
                     constexpr bool AN = decltype(aniso_tag)::value;
                     for (int i0 = wb; i0 < we; i0 += 32) {
                         const int i = i0 + lane;
                         const bool ok = i < we;
-                        const unsigned kk = skey[ok ? i : we - 1];
+                        const unsigned kk = skey[ok ? i : we - 1];    // slots beyond the range: last entry, zero coefficient
                         const float av = ok ? sval[i] : 0.f;
                         const float v2 = (!AN && ok) ? av * __ldg(wsc + (kk >> 10)) : 0.f;
                         const int m = min(32, we - i0);
@@ -636,6 +624,8 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                                         first_run = false;
                                     }
                                     cur_n = n;
+                                    xpre = __ldg(reinterpret_cast<const float2*>(xcol2 + (size_t)n * D));
+                                    gpre = __ldcg(reinterpret_cast<const float2*>(gcol + (size_t)n * D));
                                     s1 = make_float2(0.f, 0.f);
                                     s2v = make_float2(0.f, 0.f);
                                     s2 = 0.f;
@@ -656,51 +646,38 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                 if (cur_n >= 0) flush(first_run ? 0 : 1);
             }
             __syncthreads();
-            if (warp == 0) {
-                const int dl = 2 * lane;
+            if (warp == 0) {                                      // merge the parked runs by row, in list order (in place)
+                int j = -1, last = -1;
+                float2 acc = make_float2(0.f, 0.f);
+                float a2 = 0.f;
                 for (int i = 0; i < 16; ++i) {
                     const int n = prow[i];
                     if (n < 0) continue;
-                    if (dl < dc) {
-                        float2* gp = reinterpret_cast<float2*>(G + (size_t)n * pitch + dl);
-                        const float2 v = *reinterpret_cast<const float2*>(part + i * 64 + dl);
-                        float2 t = *gp;
-                        t.x += v.x;
-                        t.y += v.y;
-                        *gp = t;
-                    }
-                    if (lane == 0) g2[n] += part2[i];
+                    const float2 v = *reinterpret_cast<const float2*>(part + i * 64 + dl);
+                    const float p2 = part2[i];
+                    __syncwarp();
+                    if (n != last) { ++j; last = n; acc = make_float2(0.f, 0.f); a2 = 0.f; }
+                    acc.x += v.x; acc.y += v.y; a2 += p2;
+                    *reinterpret_cast<float2*>(part + j * 64 + dl) = acc;
+                    if (lane == 0) { part2[j] = a2; mrow[j] = n; }
                     __syncwarp();
                 }
+                if (lane == 0) mcount = j + 1;
+            }
+            __syncthreads();
+            for (int j = warp; j < mcount; j += 8) {
+                const int n = mrow[j];
+                const float2 xv = __ldg(reinterpret_cast<const float2*>(xcol2 + (size_t)n * D));
+                float2 gv = __ldcg(reinterpret_cast<const float2*>(gcol + (size_t)n * D));
+                const float2 v = *reinterpret_cast<const float2*>(part + j * 64 + dl);
+                const float p2 = part2[j];
+                gv.x += fmaf(-xv.x, p2, v.x);
+                gv.y += fmaf(-xv.y, p2, v.y);
+                if (dok2) *reinterpret_cast<float2*>(gcol + (size_t)n * D) = gv;
             }
             __syncthreads();
             if (threadIdx.x == 0) lcount = 0;
             __syncthreads();
-        }
-    }
-    __syncthreads();
-    if ((dc & 3) == 0) {
-        const int q4 = dc >> 2;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < HW * q4; i += 256) {
-            const int n = i / q4, c4 = i - n * q4;
-            const size_t go = ((size_t)b * HW + n) * D + d0 + 4 * c4;
-            float4 v = *reinterpret_cast<const float4*>(G + (size_t)n * pitch + 4 * c4);
-            const float gn = aniso ? 0.f : g2[n];               // isotropic: - xhat_n * sum_e a_e w_p applied here
-            if (gn != 0.f) {
-                const float4 xr = __ldg(reinterpret_cast<const float4*>(xhat + go));
-                v.x = fmaf(-gn, xr.x, v.x); v.y = fmaf(-gn, xr.y, v.y);
-                v.z = fmaf(-gn, xr.z, v.z); v.w = fmaf(-gn, xr.w, v.w);
-            }
-            *reinterpret_cast<float4*>(g_xhat + go) = v;
-        }
-    } else {
-        for (int n = warp; n < HW; n += 8) {
-            float* dst = g_xhat + ((size_t)b * HW + n) * D + d0;
-            const float* gr = G + (size_t)n * pitch;
-            const float* xr = xhat + ((size_t)b * HW + n) * D + d0;
-            const float gn = aniso ? 0.f : g2[n];
-            for (int d = lane; d < dc; d += 32) dst[d] = (gn != 0.f) ? fmaf(-gn, xr[d], gr[d]) : gr[d];
         }
     }
 }
@@ -875,9 +852,10 @@ extern "C" int mgp_head_bwd(const float* grad_logits, const float* logits, const
     proto_weight_kernel<<<(unsigned)((npd + 255) / 256), 256, 0, st>>>(mu, sigma, w, wm, wsc, noniso, npd, D);
     MGP_CHECK_LAUNCH();
     const int DC = 64;                                       // D-chunk per CTA: 8 warps x 8 dims
-    size_t smem = (size_t)HW * DC * 4 + (size_t)LCAP * 16 + (size_t)(9 * HW + C + T) * 4;
+    size_t smem = (size_t)LCAP * 16 + (size_t)(8 * HW + C + T) * 4;
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
     MGP_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGP_CUDA(cudaMemsetAsync(g_xhat, 0, (size_t)B * HW * D * sizeof(float), st));   // rows without mined patches stay zero
     dim3 grid(B, (D + DC - 1) / DC);
     head_bwd_kernel<<<grid, 256, smem, st>>>(grad_logits, logits, vals, idx, weight_cp, gt, xhat_nd, w, wm, wsc, noniso,
                                              g_xhat, HW, C, K, D, T, DC);

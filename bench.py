@@ -12,11 +12,14 @@ training hot path over one batch: normalise -> log-likelihood -> top-T mining ->
 The backbone is outside the path and is not timed.
 
   value   images/s, whole job, inputs resident in HBM
-  e2e     images/s through MGProto.head()/update_GMM() with HOST (pinned) feature batches: H2D of the
-          features and D2H of the logits inside the timed region, synchronised every step
+  e2e     images/s through MGProto.head()/update_GMM() with HOST (pinned) feature batches: every step's H2D of
+          its features and D2H of its logits are inside the timed region, double-buffered on copy streams
+          (mgproto_b200.pipeline) so that they overlap the neighbouring steps' compute
   roofline  the log-likelihood kernel (mgp_logprob_fwd, [N,P] output: the north-star kernel), timed
           alone with CUDA events: algorithmic bytes 4*(N*D + 2*P*D + N*P) per launch / duration,
-          against MEASURED_PEAKS.json's HBM copy bandwidth (burst figure: kernel timed alone)
+          against MEASURED_PEAKS.json's HBM copy bandwidth (burst figure: kernel timed alone);
+          roofline_step_logprob: the variant the labelled step runs (max/arg-max epilogue, log p stays on
+          chip) against the measured dense bf16 tensor peak
   cpu_baseline  the oracle port of the reference algorithm on the host cores, bounded sample
 """
 from __future__ import annotations
@@ -132,7 +135,7 @@ def _config(n_gpus):
                         "mixture, T=%d, bank %d rows/class; step = head fwd+bwd + enqueue + update_GMM"
                         % (c["B"], c["B"], c["D"], c["H"], c["W"], c["C"], c["K"], c["D"], c["T"], c["cap"]),
             "global_batch": c["B"] * n_gpus, "parallelism": "dp%d (image-sharded, EM stats all-reduce)" % n_gpus,
-            "l2": "inputs rotate through %d distinct batches (%.0f MB) + 401 MB intermediate > 126 MB L2"
+            "l2": "inputs rotate through %d distinct batches (%.0f MB) > 126 MB L2; the labelled step keeps log p on chip (no [B,P,HW] intermediate)"
                   % (N_ROT, N_ROT * c["B"] * c["D"] * c["H"] * c["W"] * 4 / 1e6)}
 
 
@@ -285,22 +288,27 @@ def main():
     value = B * world * args.steps / (ms / 1e3)
 
     # ---- end to end: host buffers in, logits out ---------------------------------------------
-    x_dev = torch.empty(B, D, H, Wd, device=dev)
-    out_host = torch.empty(B, c["C"], c["T"], pin_memory=True)
+    # every step copies its own pinned-host feature batch to the device and reads its logits back to pinned host
+    # memory; mgproto_b200.pipeline double-buffers both so the copies of neighbouring steps overlap the compute
+    from mgproto_b200.pipeline import HostFeeder, HostSink
+    feeder = HostFeeder((B, D, H, Wd), dev, depth=2)
+    sink = HostSink((B, c["C"], c["T"]), depth=2, device=dev)
 
-    def e2e_step(i):
-        x_dev.requires_grad_(False)
-        x_dev.copy_(feats_host[i % N_ROT], non_blocking=True)
-        out = step(x_dev, gts[i % N_ROT])
-        out_host.copy_(out.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def e2e_run(n):
+        feeder.stage(feats_host[0])
+        for i in range(n):
+            if i + 1 < n:
+                feeder.stage(feats_host[(i + 1) % N_ROT])
+            x_dev = feeder.acquire()
+            out = step(x_dev, gts[i % N_ROT])
+            sink.put(out.detach())
+            feeder.release(x_dev)
+        sink.wait()
 
-    for i in range(3):
-        e2e_step(i)
+    e2e_run(3)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     e1.record()
     barrier()
     tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -357,6 +365,26 @@ def main():
                                         "achieved": abytes / t_op / 1e9, "peak": peak, "unit": "GB/s",
                                         "frac": abytes / t_op / 1e9 / peak, "us_per_launch": t_op * 1e6}
         del outs
+        # the variant the labelled step runs: same GEMM, max/arg-max epilogue, no log p output -> tensor-bound
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops") if \
+            os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+        tpk, tsrc = (pk, "MEASURED_PEAKS.json bf16_tflops (burst)") if pk else (2250.0, "nominal dense bf16 (B200_PROFILING.md fallback)")
+        if args.math != "fp32" and _lib.load().mgp_has_tensor_core_path():
+            w1 = [ops.logprob_top1(xs[i], mu, sg, B, HW, "tc", return_ws=True)[1] for i in range(6)]
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(reps):
+                ops.logprob_top1(xs[i % 6], mu, sg, B, HW, "tc_reuse", ws=w1[i % 6])
+            e1.record()
+            torch.cuda.synchronize()
+            t_t1 = e0.elapsed_time(e1) / reps / 1e3
+            fl = 3 * 2.0 * N * P * D                                  # three fp16 passes of the K = D GEMM (isotropic sigma)
+            extra["roofline_step_logprob"] = {
+                "kernel": "logprob_tc_kernel<top1> (in-step variant: 4 MB memset + GEMM with max/arg-max epilogue, no [N,P] store)",
+                "bound": "tensor", "achieved": fl / t_t1 / 1e12, "peak": tpk, "unit": "TFLOP/s",
+                "frac": fl / t_t1 / 1e12 / tpk, "peak_source": tsrc, "us_per_launch": t_t1 * 1e6,
+                "pairs_per_sec": N * P / t_t1, "algorithmic_GBps_equiv": abytes / t_t1 / 1e9}
+            del w1
         # EM statistics kernel, same treatment (second kernel the north star names)
         order = torch.arange(c["C"], dtype=torch.int32, device=dev)
         stats = torch.empty(c["C"], net.em_n_split, ops.em_stat_stride(c["K"], D), device=dev)

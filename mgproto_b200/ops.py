@@ -123,7 +123,7 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
     return (out, ws) if return_ws else out
 
 
-def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto"):
+def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto", ws=None, return_ws=False):
     """Per (image, prototype) max / arg-max of log p over the patches, computed in the tensor-core kernel's
     epilogue without writing log p (MGP_OUT_TOP1_BP).  -> packed int64 [B,P] (see include/mgproto_b200.h), or None
     when the tensor-core path does not cover the shape / math mode (the caller then materialises log p)."""
@@ -137,19 +137,22 @@ def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto"):
     m = _math(math)
     if m == MGP_MATH_AUTO and D > 128:
         m = MGP_MATH_TC_ISO if (D == 256 and sigma_is_isotropic(sg)) else MGP_MATH_FP32
-    if m == MGP_MATH_FP32 or m == MGP_MATH_TC_REUSE:
+    if m == MGP_MATH_FP32 or (m == MGP_MATH_TC_REUSE and ws is None):
         return None
     lib = _lib.load()
     nbytes = lib.mgp_logprob_ws_bytes(B, HW, P, D, m)
-    ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
+    if ws is None:
+        ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
+    elif ws.numel() < nbytes:
+        raise RuntimeError("mgproto_b200: workspace too small")
     best = torch.empty((B, P), device=x.device, dtype=torch.int64)
     rc = lib.mgp_logprob_fwd(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), 0.0, 0.0, best.data_ptr(), MGP_OUT_TOP1_BP,
                              B, HW, P, D, m, ws.data_ptr(), nbytes, _stream())
     if rc == -2:                                      # MGP_ERR_UNSUPPORTED: no tensor-core path for this shape
         return None
     check(rc, "mgp_logprob_fwd(top1)")
-    _count(4)
-    return best
+    _count(1 if m == MGP_MATH_TC_REUSE else 3)
+    return (best, ws) if return_ws else best
 
 
 def head_select_top1(best, xhat_nd, mu_pd, sigma_pd, weight_cp, gt, T, C, K, HW):
@@ -348,7 +351,9 @@ def update_gmm(bank, updated, mem_len, mu_ckd, sigma_ckd, weight_cp, exp_avg, ex
                                      adam_step.data_ptr(), order.data_ptr(), sched.data_ptr(), stats.data_ptr(),
                                      int(n_split), int(num_em_loop), float(alpha), float(lr), float(beta1), float(beta2),
                                      float(adam_eps), float(tau), float(lamda), C, K, D, cap, _stream()), "mgp_update_gmm")
-    _count(3 + 2 * int(num_em_loop))
+    import os
+    fused = 2 <= K <= 16 and D in (64, 128) and cap >= 2 and os.environ.get("MGP_EM_UNFUSED") is None
+    _count(2 if fused else 3 + 2 * int(num_em_loop))
 
 
 def em_estep(x_nd, mu_kd, sigma_kd, pi_k, want_log_resp=True, want_score=True):

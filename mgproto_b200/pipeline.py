@@ -1,0 +1,80 @@
+"""Host <-> device staging around the hot path (the reference's DataLoader + ``.cuda()`` + ``.cpu()`` glue,
+train_and_test.py:24-34): double-buffered so that the host->device copy of batch i+1 and the device->host read of
+batch i's logits overlap the compute of batch i.  Plain CUDA streams and events; nothing here touches the kernels."""
+from __future__ import annotations
+
+import torch
+
+
+class HostFeeder:
+    """``depth`` device buffers fed from pinned host tensors on a copy stream.
+
+        feeder.stage(x_host)            # enqueue the H2D copy of a batch (call one batch ahead)
+        x = feeder.acquire()            # device tensor of the oldest staged batch; the current stream waits for its copy
+        ... launch work reading x on the current stream ...
+        feeder.release(x)               # the buffer may be overwritten once that work has finished
+    """
+
+    def __init__(self, shape, device, dtype=torch.float32, depth: int = 2):
+        self.bufs = [torch.empty(shape, device=device, dtype=dtype) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [None] * depth
+        self.staged = []            # indices in FIFO order
+        self.next = 0
+
+    def stage(self, x_host: torch.Tensor):
+        i = self.next
+        self.next = (self.next + 1) % len(self.bufs)
+        if i in self.staged:
+            raise RuntimeError("mgproto_b200: HostFeeder overrun (stage() called more than `depth` batches ahead)")
+        buf = self.bufs[i]
+        buf.requires_grad_(False)
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[i] is not None:
+                self.copy_stream.wait_event(self.free[i])
+            buf.copy_(x_host, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self.staged.append(i)
+
+    def acquire(self) -> torch.Tensor:
+        i = self.staged.pop(0)
+        torch.cuda.current_stream().wait_event(self.ready[i])
+        return self.bufs[i]
+
+    def release(self, buf: torch.Tensor):
+        i = next(k for k, b in enumerate(self.bufs) if b is buf)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.free[i] = ev
+
+
+class HostSink:
+    """Device -> pinned host copies on their own stream (``depth`` host buffers, reused round-robin)."""
+
+    def __init__(self, shape, dtype=torch.float32, depth: int = 2, device=None):
+        self.bufs = [torch.empty(shape, dtype=dtype, pin_memory=True) for _ in range(depth)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.done = [None] * depth
+        self.next = 0
+
+    def put(self, t_dev: torch.Tensor) -> torch.Tensor:
+        """Enqueue the read-back of ``t_dev`` (produced on the current stream); returns the host buffer it lands in
+        (valid after ``wait()`` or once its event has completed)."""
+        i = self.next
+        self.next = (self.next + 1) % len(self.bufs)
+        produced = torch.cuda.Event()
+        produced.record(torch.cuda.current_stream())
+        if self.done[i] is not None:
+            self.done[i].synchronize()                 # the host buffer is about to be overwritten
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(produced)
+            self.bufs[i].copy_(t_dev, non_blocking=True)
+            t_dev.record_stream(self.stream)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.done[i] = ev
+        return self.bufs[i]
+
+    def wait(self):
+        self.stream.synchronize()

@@ -546,3 +546,26 @@ def test_fused_top1_path_vs_materialised(B, H, W, C, K, D, T, aniso):
     out.backward(gl)
     torch.testing.assert_close(out.detach(), lg0, rtol=RTOL, atol=1e-6)
     assert torch.isfinite(xa.grad).all()
+
+
+@pytest.mark.gpu
+def test_host_pipeline_roundtrip():
+    """pipeline.HostFeeder / HostSink: staged copies arrive intact and in order while work is queued behind them."""
+    from mgproto_b200.pipeline import HostFeeder, HostSink
+    dev = _dev()
+    hosts = [torch.full((4, 8), float(i)).pin_memory() for i in range(7)]
+    feeder = HostFeeder((4, 8), dev, depth=2)
+    sink = HostSink((4, 8), depth=2, device=dev)
+    got = []
+    feeder.stage(hosts[0])
+    for i in range(7):
+        if i + 1 < 7:
+            feeder.stage(hosts[i + 1])
+        x = feeder.acquire()
+        y = x * 2 + 1
+        h = sink.put(y)
+        feeder.release(x)
+        sink.wait()
+        got.append(h.clone())
+    for i, h in enumerate(got):
+        assert torch.equal(h, torch.full((4, 8), 2.0 * i + 1))

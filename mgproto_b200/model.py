@@ -110,7 +110,8 @@ class MGProto(nn.Module):
         # B200 knobs (not in the reference)
         self.math_mode = "auto"          # 'fp32' exact SIMT | 'tc' tcgen05 fp16x3 | 'auto'
         self.em_n_split = 2              # row splits of the EM statistics reduction
-        self.em_group = None             # torch.distributed process group for the sharded EM (parallel.py)
+        self.em_group = None             # torch.distributed process group of the batch-sharded replicas (parallel.py)
+        self.em_shard = False            # True: shard bank rows over the ranks + all-reduce the EM statistics per loop
         self._adam_step_dev = None       # int32[1] on the device: Adam step count, advanced by update_GMM's planner
         self._adam_step_seen = None      # host value the device counter was seeded from / last folded back to
         self._em_dirty = False           # device counter ahead of prototype_optimizer.state[...]['step']
@@ -241,7 +242,7 @@ class MGProto(nn.Module):
         order = torch.empty(C, dtype=torch.int32, device=dev)
         sched = torch.empty(2, dtype=torch.int32, device=dev)
         world, rank = 1, 0
-        if self.em_group is not None:
+        if self.em_group is not None and self.em_shard:
             import torch.distributed as dist
             world, rank = dist.get_world_size(self.em_group), dist.get_rank(self.em_group)
         n_split = self.em_n_split if world == 1 else 1

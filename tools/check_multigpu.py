@@ -33,6 +33,7 @@ def main():
     C, K, D, T, cap, H, W = 12, 5, 128, 8, 16, 14, 14
     Bg = 8 * world
     net = parallel.attach(make(dev, C, K, D, T, cap))
+    net.em_shard = len(sys.argv) > 1 and sys.argv[1] == "shard"      # default: every rank runs the whole EM on its replica
     ref = make(dev, C, K, D, T, cap) if rank == 0 else None
     g = torch.Generator().manual_seed(3)
     ok = True
@@ -61,7 +62,7 @@ def main():
     same = torch.tensor([float(torch.equal(t, net.prototype_means.detach()))], device=dev)
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("multi-gpu parity:", "OK" if ok else "MISMATCH", "| replicas identical:", bool(same.item()),
+        print("em_shard", net.em_shard, "multi-gpu parity:", "OK" if ok else "MISMATCH", "| replicas identical:", bool(same.item()),
               "| mem_len", net.queue.mem_len.tolist())
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -257,17 +257,34 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
     float* s_mu = sm + ((P + K * T + K * HWp + 3) & ~3);   // [K][D], 16-byte aligned
     float* s_ri = s_mu + K * D;          // [K][D]   1/sigma
     float* s_ls = s_ri + K * D;          // [K]      sum_d log sigma
+    float* s_mm = s_ls + K;              // [K]      |mu_k|^2
+    float* s_wd = s_mm + K;              // [P]      pi_p = last_layer.weight[c, c*K + k]
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long g = gt[b];
     const bool gok = (g >= 0 && g < C);
 
-    for (int p = threadIdx.x; p < P; p += 256) {
-        const unsigned long long pk = best[(size_t)b * P + p];
-        const float e = expf(key2f((unsigned)(pk >> 32)));                       // ref model.py:215
-        win0[p] = e;
-        vals[((size_t)b * P + p) * T] = e;
-        idx[((size_t)b * P + p) * T] = (int)(0xffffffffu - (unsigned)(pk & 0xffffffffull));
+    // (all loads of a thread are issued before their first use: the kernel is a chain of L2 latencies otherwise)
+    for (int p0 = threadIdx.x; p0 < P; p0 += 256 * 4) {
+        unsigned long long pk[4];
+        float wd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + 256 * u;
+            pk[u] = (p < P) ? best[(size_t)b * P + p] : 0ull;
+            wd[u] = (p < P) ? __ldg(weight + (size_t)(p / K) * P + p) : 0.f;     // class-diagonal block of last_layer.weight
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + 256 * u;
+            if (p < P) {
+                const float e = expf(key2f((unsigned)(pk[u] >> 32)));            // ref model.py:215
+                win0[p] = e;
+                s_wd[p] = wd[u];
+                vals[((size_t)b * P + p) * T] = e;
+                idx[((size_t)b * P + p) * T] = (int)(0xffffffffu - (unsigned)(pk[u] & 0xffffffffull));
+            }
+        }
     }
     if (gok) {
         const float* mug = mu + (size_t)g * K * D;
@@ -284,6 +301,18 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
         }
         __syncthreads();
         // log p[n,k] = -D/2 log 2pi - sum log sigma - 1/2 sum ((x-mu)/sigma)^2   (ref model.py:256-275, exact form)
+        // sigma constant over d inside each of the K prototypes (every state the shipped loop reaches)?  Then
+        // sum ((x-mu)/sigma)^2 = w (|x|^2 - 2 x.mu + |mu|^2): one FMA per element instead of three operations
+        bool same = true;
+        for (int i = threadIdx.x; i < K * D; i += 256) same = same && (s_ri[i] == s_ri[(i / D) * D]);
+        const bool iso = __syncthreads_and(same ? 1 : 0) != 0;
+        for (int k = warp; k < K; k += 8) {
+            float mm = 0.f;
+            for (int d = lane; d < D; d += 32) mm = fmaf(s_mu[k * D + d], s_mu[k * D + d], mm);
+            mm = warp_sum(mm);
+            if (lane == 0) s_mm[k] = mm;
+        }
+        __syncthreads();
         // thread = (patch n, half of the prototypes): eight 16-byte loads of the patch row are in flight at a time
         // (the row is read once; prototype rows are shared-memory broadcasts)
         const int KHh = (K + 1) / 2;
@@ -292,24 +321,53 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
             const float4* xr = reinterpret_cast<const float4*>(xhat + ((size_t)b * HW + n) * D);
             for (int k0 = kb; k0 < ke; k0 += 5) {
                 float q[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                float2 q2[5], xx2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) q2[i] = make_float2(0.f, 0.f);
                 for (int d0 = 0; d0 < D / 4; d0 += 8) {
                     float4 xv[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) xv[u] = (d0 + u < D / 4) ? __ldg(xr + d0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (iso) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (d0 + u >= D / 4) break;
+                        for (int u = 0; u < 8; ++u) {
+                            if (d0 + u >= D / 4) break;
+                            const float2 x01 = make_float2(xv[u].x, xv[u].y), x23 = make_float2(xv[u].z, xv[u].w);
+                            xx2 = ffma2(x01, x01, xx2);
+                            xx2 = ffma2(x23, x23, xx2);
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) {
-                            const int k = min(k0 + i, K - 1);
-                            const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + 4 * (d0 + u));
-                            const float4 r = *reinterpret_cast<const float4*>(s_ri + k * D + 4 * (d0 + u));
-                            float t;
-                            t = (xv[u].x - m.x) * r.x; q[i] = fmaf(t, t, q[i]);
-                            t = (xv[u].y - m.y) * r.y; q[i] = fmaf(t, t, q[i]);
-                            t = (xv[u].z - m.z) * r.z; q[i] = fmaf(t, t, q[i]);
-                            t = (xv[u].w - m.w) * r.w; q[i] = fmaf(t, t, q[i]);
+                            for (int i = 0; i < 5; ++i) {
+                                const int k = min(k0 + i, K - 1);
+                                const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + 4 * (d0 + u));
+                                q2[i] = ffma2(x01, make_float2(m.x, m.y), q2[i]);
+                                q2[i] = ffma2(x23, make_float2(m.z, m.w), q2[i]);
+                            }
                         }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (d0 + u >= D / 4) break;
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) {
+                                const int k = min(k0 + i, K - 1);
+                                const float4 m = *reinterpret_cast<const float4*>(s_mu + k * D + 4 * (d0 + u));
+                                const float4 r = *reinterpret_cast<const float4*>(s_ri + k * D + 4 * (d0 + u));
+                                float t;
+                                t = (xv[u].x - m.x) * r.x; q[i] = fmaf(t, t, q[i]);
+                                t = (xv[u].y - m.y) * r.y; q[i] = fmaf(t, t, q[i]);
+                                t = (xv[u].z - m.z) * r.z; q[i] = fmaf(t, t, q[i]);
+                                t = (xv[u].w - m.w) * r.w; q[i] = fmaf(t, t, q[i]);
+                            }
+                        }
+                    }
+                }
+                if (iso) {
+                    const float xx = xx2.x + xx2.y;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int k = min(k0 + i, K - 1);
+                        const float ri = s_ri[k * D];
+                        q[i] = ri * ri * (xx - 2.0f * (q2[i].x + q2[i].y) + s_mm[k]);
                     }
                 }
 #pragma unroll
@@ -342,10 +400,9 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
     __syncthreads();
     for (int e = threadIdx.x; e < C * T; e += 256) {
         const int c = e / T, t = e - c * T;
-        const float* wrow = weight + (size_t)c * P + (size_t)c * K;            // class-diagonal block of last_layer.weight
         const bool own = gok && (long long)c == g;
         float s = 0.f;
-        for (int k = 0; k < K; ++k) s = fmaf(__ldg(wrow + k), own ? winT[k * T + t] : win0[c * K + k], s);
+        for (int k = 0; k < K; ++k) s = fmaf(s_wd[c * K + k], own ? winT[k * T + t] : win0[c * K + k], s);
         logits[((size_t)b * C + c) * T + t] = logf(s);                         // ref model.py:222, :254
     }
 }
@@ -805,7 +862,7 @@ extern "C" int mgp_head_select_top1(const uint64_t* best, const float* xhat_nd, 
     if (B <= 0 || HW <= 0 || C <= 0 || K <= 0 || D <= 0 || T <= 0 || (D & 3)) return MGP_ERR_INVALID;
     if (T > 32 || T > HW || HW > 1024) return MGP_ERR_UNSUPPORTED;
     const int P = C * K;
-    const size_t smem = ((size_t)P + (size_t)K * T + (size_t)K * (HW + 1) + (size_t)2 * K * D + K + 4) * sizeof(float);
+    const size_t smem = ((size_t)2 * P + (size_t)K * T + (size_t)K * (HW + 1) + (size_t)2 * K * D + 2 * K + 4) * sizeof(float);
     if (smem > 200 * 1024) return MGP_ERR_UNSUPPORTED;
     const int R = (HW + 31) / 32;
     cudaStream_t st = (cudaStream_t)stream;

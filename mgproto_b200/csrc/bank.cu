@@ -73,38 +73,77 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
         }
     }
     __syncthreads();
-    // warp per image: rows of the same class in earlier images (offset) and in the whole batch (total)
+    // Offsets inside a class follow image order.  Two equivalent schedules, O(min(C, B) * B / 32) warp steps:
+    //   class-major (C <= B): a warp scans the batch for its class and hands out running offsets (ballot prefix);
+    //   image-major (B <  C): a warp sums, for its image, the rows of the same class in earlier images.
+    // offs[b] = rows of cls[b] accepted before image b; ctot[b] = rows of cls[b] in the whole batch, stored as
+    // -(total) - 1 for the first image of its class (that image publishes the new mem_len / head).
+    int* offs = wr_m;            // [B]
+    int* ctot = sm + 3 * B;      // [B]
+    if (C <= B) {
+        for (int c = warp; c < C; c += nwarp) {
+            int off = 0, firstb = -1;
+            for (int b0 = 0; b0 < B; b0 += 32) {
+                const int b = b0 + lane;
+                const bool mine = (b < B) && (cls[b] == c);
+                const unsigned mm = __ballot_sync(0xffffffffu, mine);
+                if (firstb < 0 && mm) firstb = b0 + __ffs(mm) - 1;
+                int u = mine ? ucount[b] : 0;
+                int incl = u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (mine) offs[b] = off + incl - u;
+                off += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            for (int b0 = 0; b0 < B; b0 += 32) {
+                const int b = b0 + lane;
+                if (b < B && cls[b] == c) ctot[b] = (b == firstb) ? -off - 1 : off;
+            }
+        }
+    } else {
+        for (int b = warp; b < B; b += nwarp) {
+            const int c = cls[b];
+            if (c < 0) continue;
+            int off = 0, tot = 0, earlier = 0;
+            for (int b2 = lane; b2 < B; b2 += 32) {
+                if (cls[b2] == c) {
+                    const int u = ucount[b2];
+                    tot += u;
+                    if (b2 < b) { off += u; earlier = 1; }
+                }
+            }
+            off = __reduce_add_sync(0xffffffffu, off);
+            tot = __reduce_add_sync(0xffffffffu, tot);
+            earlier = __reduce_add_sync(0xffffffffu, earlier);
+            if (lane == 0) { offs[b] = off; ctot[b] = earlier ? tot : -tot - 1; }
+        }
+    }
+    __syncthreads();
     for (int b = warp; b < B; b += nwarp) {
         const int c = cls[b];
         if (c < 0) continue;
-        int off = 0, tot = 0, earlier = 0;
-        for (int b2 = lane; b2 < B; b2 += 32) {
-            if (cls[b2] == c) {
-                const int u = ucount[b2];
-                tot += u;
-                if (b2 < b) { off += u; earlier = 1; }
-            }
-        }
-        off = __reduce_add_sync(0xffffffffu, off);
-        tot = __reduce_add_sync(0xffffffffu, tot);
-        const bool first_of_class = __reduce_add_sync(0xffffffffu, earlier) == 0;
+        const int off = offs[b];
+        const int ct = ctot[b];
+        const int m = min(ct < 0 ? -ct - 1 : ct, cap);
         const int len = (int)mem_len[c];
         const int hd = head[c];
-        const int m = min(tot, cap);
         for (int k = lane; k < K; k += 32) {
             const int r = plan[b * K + k];
             int slot = -1;
             if (r >= 0 && off + r < m) slot = (hd + len + off + r) % cap;
             plan[b * K + k] = slot;
         }
-        // every reader of mem_len/head for class c sees the same old values; publish after the barrier
-        if (lane == 0) wr_m[b] = first_of_class ? m : -1;
     }
-    __syncthreads();
+    __syncthreads();       // every reader of mem_len / head has seen the old values
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const int c = cls[b];
         if (c < 0) continue;
-        const int m = wr_m[b];
+        const int ct = ctot[b];
+        if (ct >= 0) continue;                                             // not the first image of its class
+        const int m = min(-ct - 1, cap);
         if (m <= 0) continue;
         const int len = (int)mem_len[c];
         const int hd = head[c];
@@ -188,7 +227,7 @@ extern "C" int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, ui
     if (B <= 0 || C <= 0 || K <= 0 || D <= 0 || cap <= 0 || (D & 3)) return MGP_ERR_INVALID;
     if (B > 8192 || K > 64) return MGP_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = (size_t)3 * B * sizeof(int);
+    size_t smem = (size_t)4 * B * sizeof(int);
     MGP_CUDA(cudaFuncSetAttribute(enqueue_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     enqueue_plan_kernel<<<1, 1024, smem, st>>>(mem_len, head, updated, top1, gt, plan, B, C, K, cap);
     MGP_CHECK_LAUNCH();

@@ -112,6 +112,10 @@ class MGProto(nn.Module):
         self.em_n_split = 2              # row splits of the EM statistics reduction
         self.em_group = None             # torch.distributed process group of the batch-sharded replicas (parallel.py)
         self.em_shard = False            # True: shard bank rows over the ranks + all-reduce the EM statistics per loop
+        self.overlap_enqueue = True      # multi-GPU: all-gather + enqueue on a side stream, behind the backward
+        self._side_stream = None
+        self._enqueue_done = None
+        self._keepalive = None
         self._adam_step_dev = None       # int32[1] on the device: Adam step count, advanced by update_GMM's planner
         self._adam_step_seen = None      # host value the device counter was seeded from / last folded back to
         self._em_dirty = False           # device counter ahead of prototype_optimizer.state[...]['step']
@@ -119,6 +123,7 @@ class MGProto(nn.Module):
     # -- reference attribute: CPU bool flags ----------------------------------------------------
     @property
     def memory_updated_cls(self):
+        self.wait_enqueue()
         return self.queue.updated.bool().cpu()
 
     # -- backbone side (stock PyTorch) ----------------------------------------------------------
@@ -141,10 +146,31 @@ class MGProto(nn.Module):
                 gt = gt.contiguous()
                 top1, rows = ops.mined_gather(xhat, idx, gt, x_add.shape[2] * x_add.shape[3], self.num_classes,
                                               self.num_prototypes_per_class)
-                if self.em_group is not None:                                     # batch-sharded replicas
+                if self.em_group is not None and self.overlap_enqueue:
+                    # batch-sharded replicas: the exchange of the mined rows and the enqueue run on a side stream and
+                    # overlap this step's loss / backward (nothing there reads the bank); update_GMM waits for them.
+                    # The inputs stay referenced until the main stream has waited (no record_stream: that would park
+                    # their blocks in the allocator's deferred-free list and force fresh cudaMallocs every step).
                     from .parallel import all_gather_mined
-                    top1, rows, gt = all_gather_mined(top1, rows, gt, self.em_group)
-                ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, rows, top1, gt)
+                    self.wait_enqueue()
+                    cur = torch.cuda.current_stream()
+                    if self._side_stream is None:
+                        self._side_stream = torch.cuda.Stream(device=x_add.device)
+                    side = self._side_stream
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        t1, r1, g1 = all_gather_mined(top1, rows, gt, self.em_group)
+                        ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, r1, t1, g1)
+                        done = torch.cuda.Event()
+                        done.record(side)
+                        del t1, r1, g1                                            # side-stream blocks: reused in stream order
+                    self._enqueue_done = done
+                    self._keepalive = (top1, rows, gt)
+                else:
+                    if self.em_group is not None:                                 # batch-sharded replicas
+                        from .parallel import all_gather_mined
+                        top1, rows, gt = all_gather_mined(top1, rows, gt, self.em_group)
+                    ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, rows, top1, gt)
                 self.iteration_counter += 1                                       # ref :252
         return logits
 
@@ -204,6 +230,14 @@ class MGProto(nn.Module):
             return None
         return g
 
+    def wait_enqueue(self):
+        """Make the current stream wait for a bank enqueue still running on the side stream (multi-GPU path).
+        update_GMM and the next enqueue call it; call it before reading ``queue`` tensors on another stream."""
+        if self._enqueue_done is not None:
+            torch.cuda.current_stream().wait_event(self._enqueue_done)
+            self._enqueue_done = None
+            self._keepalive = None
+
     def sync_optimizer_state(self):
         """Fold the Adam step count kept on the device (advanced by every update_GMM without touching the host)
         into ``prototype_optimizer.state[...]['step']``.  Synchronises; call it before inspecting or saving the
@@ -234,6 +268,7 @@ class MGProto(nn.Module):
         synchronisation.  With ``em_group`` set, bank rows are sharded over the ranks and the packed
         sufficient statistics are all-reduced once per EM loop (parallel.py)."""
         q = self.queue
+        self.wait_enqueue()
         C, K, D = self.prototype_means.shape
         cap = q.cap_cls
         dev = self.prototype_means.device

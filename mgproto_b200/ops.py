@@ -6,6 +6,8 @@ stream through ctypes.  Nothing falls back to ATen or to the CPU.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -351,7 +353,6 @@ def update_gmm(bank, updated, mem_len, mu_ckd, sigma_ckd, weight_cp, exp_avg, ex
                                      adam_step.data_ptr(), order.data_ptr(), sched.data_ptr(), stats.data_ptr(),
                                      int(n_split), int(num_em_loop), float(alpha), float(lr), float(beta1), float(beta2),
                                      float(adam_eps), float(tau), float(lamda), C, K, D, cap, _stream()), "mgp_update_gmm")
-    import os
     fused = 2 <= K <= 16 and D in (64, 128) and cap >= 2 and os.environ.get("MGP_EM_UNFUSED") is None
     _count(2 if fused else 3 + 2 * int(num_em_loop))
 

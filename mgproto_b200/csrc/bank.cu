@@ -74,13 +74,14 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
     }
     __syncthreads();
     // Offsets inside a class follow image order.  Two equivalent schedules, O(min(C, B) * B / 32) warp steps:
-    //   class-major (C <= B): a warp scans the batch for its class and hands out running offsets (ballot prefix);
-    //   image-major (B <  C): a warp sums, for its image, the rows of the same class in earlier images.
+    //   class-major (large batches, e.g. the all-gathered global batch): a warp scans the batch for its class and
+    //                hands out running offsets (prefix scan), ~45 instructions per (class, 32 images);
+    //   image-major: a warp sums, for its image, the rows of the same class in earlier images, ~10 per (image, 32 images).
     // offs[b] = rows of cls[b] accepted before image b; ctot[b] = rows of cls[b] in the whole batch, stored as
     // -(total) - 1 for the first image of its class (that image publishes the new mem_len / head).
     int* offs = wr_m;            // [B]
     int* ctot = sm + 3 * B;      // [B]
-    if (C <= B) {
+    if (9 * C <= 2 * B) {
         for (int c = warp; c < C; c += nwarp) {
             int off = 0, firstb = -1;
             for (int b0 = 0; b0 < B; b0 += 32) {

@@ -174,6 +174,12 @@ class MGProto(nn.Module):
                 self.iteration_counter += 1                                       # ref :252
         return logits
 
+    @torch.no_grad()
+    def head_level0(self, x_add):
+        """[B,C] level-0 log evidences = head(x_add, None)[:, :, 0]: what the reference's test / OoD loop uses
+        (train_and_test.py:182-199), without mining the other T-1 levels or materialising log p."""
+        return ops.head_level0(x_add, self.prototype_means, self.prototype_covs, self.last_layer.weight, self.math_mode)
+
     def forward(self, x, gt):
         """ref model.py:208-254 -> (log_probs [B,C,T], x_embed [B,sz_embedding])."""
         x_add, x_embed = self.conv_features(x)

@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, MGP_MATH_TC_REUSE, MGP_OUT_LOGP_BPHW,
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP, check)
 
-__all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
+__all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_level0", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
            "bank_linearize", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
@@ -255,6 +255,26 @@ class HeadFunction(torch.autograd.Function):
               "mgp_head_bwd")
         _count(3)
         return gx, None, None, None, None, None, None
+
+
+def head_level0(x_add, mu_ckd, sigma_ckd, weight_cp, math="auto"):
+    """Level 0 of the unlabelled head, [B,C] = head_forward(..., gt=None)[0][:, :, 0] -- all the reference's test /
+    OoD loop reads (train_and_test.py:182-199: output[:, :, 0]).  Uses the max/arg-max epilogue (no log p matrix, no
+    top-T) when the tensor-core path covers the shape; no gradient."""
+    C, K, D = mu_ckd.shape
+    B, _, H, W = x_add.shape
+    HW = H * W
+    with torch.no_grad():
+        mu = mu_ckd.detach().reshape(C * K, D).contiguous()
+        sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
+        wt = weight_cp.detach().contiguous()
+        xhat, _, _ = normalize_fwd(x_add.detach().contiguous())
+        best = logprob_top1(xhat, mu, sg, B, HW, math)
+        if best is None:
+            lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)
+            return head_select(lp, wt, None, 1, C, K)[0][:, :, 0]
+        none = torch.full((B,), -1, dtype=torch.int64, device=x_add.device)     # no own class: every class keeps level 0 only
+        return head_select_top1(best, xhat, mu, sg, wt, none, 1, C, K, HW)[0][:, :, 0]
 
 
 def head_forward(x_add, mu_ckd, sigma_ckd, weight_cp, gt, T, math="auto"):

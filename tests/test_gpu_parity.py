@@ -569,3 +569,21 @@ def test_host_pipeline_roundtrip():
         got.append(h.clone())
     for i, h in enumerate(got):
         assert torch.equal(h, torch.full((4, 8), 2.0 * i + 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math", ["auto", "fp32"])
+def test_head_level0_matches_unlabelled_head(golden, math):
+    """f2: the test / OoD loop's output[:, :, 0] (ref train_and_test.py:182-199) from the max/arg-max path equals
+    level 0 of the full unlabelled head."""
+    from mgproto_b200 import ops
+    g = golden
+    net = _model_from(g, math)
+    net.prototype_means.data.copy_(_t(g["it0_mu"]))
+    x = _t(g["it0_x_add"])
+    with torch.no_grad():
+        full, _, _ = ops.head_forward(x, net.prototype_means, net.prototype_covs, net.last_layer.weight, None,
+                                      net.mine_T, math)
+        l0 = net.head_level0(x)
+    np.testing.assert_allclose(l0.cpu().numpy(), full[:, :, 0].cpu().numpy(), rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(l0.cpu().numpy(), g["it0_logits_nogt"][:, :, 0], rtol=RTOL, atol=1e-6)

@@ -383,7 +383,13 @@ def main():
                 "kernel": "logprob_tc_kernel<top1> (in-step variant: 4 MB memset + GEMM with max/arg-max epilogue, no [N,P] store)",
                 "bound": "tensor", "achieved": fl / t_t1 / 1e12, "peak": tpk, "unit": "TFLOP/s",
                 "frac": fl / t_t1 / 1e12 / tpk, "peak_source": tsrc, "us_per_launch": t_t1 * 1e6,
-                "pairs_per_sec": N * P / t_t1, "algorithmic_GBps_equiv": abytes / t_t1 / 1e9}
+                "pairs_per_sec": N * P / t_t1, "algorithmic_GBps_equiv": abytes / t_t1 / 1e9,
+                # SURVEY 8(d) K-B (fused head, no [N,P] in HBM): its algorithmic bytes and the sustained tensor figure
+                "kb_algorithmic_bytes": 4.0 * N * D + 8.0 * P * D + 8.0 * B * P * c["T"] + 4.0 * B * c["C"] * c["T"]
+                                        + 4.0 * B * c["K"] * D,
+                "kb_GBps": (4.0 * N * D + 8.0 * P * D + 8.0 * B * P * c["T"] + 4.0 * B * c["C"] * c["T"]
+                            + 4.0 * B * c["K"] * D) / t_t1 / 1e9,
+                "frac_of_sustained_bf16": fl / t_t1 / 1e12 / 1431.0}
             del w1
         # EM statistics kernel, same treatment (second kernel the north star names)
         order = torch.arange(c["C"], dtype=torch.int32, device=dev)

@@ -3,8 +3,10 @@
 //
 // The reference runs, per updated class and EM loop, ~100 small ATen launches plus an autograd
 // backward and an Adam step over the whole [C,K,D] mean tensor (~40k launches per iteration at
-// B=256).  Here one iteration's update_GMM is 2 + 2*num_em_loop + 1 launches, independent of
-// the number of classes, with identical sequential semantics:
+// B=256).  Here one iteration's update_GMM is em_plan + ONE cluster kernel (em_fused_kernel: a class's whole
+// timeline on chip; single replica, K <= 16, D in {64,128}), or -- row-sharded multi-GPU, other shapes,
+// MGP_EM_UNFUSED=1 -- 2 + 2*num_em_loop + 1 launches, independent of the number of classes, with identical
+// sequential semantics:
 //
 //   em_plan            active[c] = updated[c] && bank full; order[c] = rank among active
 //   em_update phase 0  leading zero-gradient Adam steps of every class

@@ -1,5 +1,6 @@
 // a4-a7: top-T prototype mining over the patches of each image, wrong-class rule, block-diagonal
-// pi mix and log; its backward; and the push-projection argmin (f1).
+// pi mix and log (head_select_kernel: from a materialised log p; head_top1_kernel: labelled step, from the
+// tensor-core epilogue's packed max/arg-max); its backward; the fused loss; the push-projection argmin (f1).
 // ref: model.py:188-206, :214-222, :254, :54-74; push.py:125-158.
 #include "mgp_common.cuh"
 #include <type_traits>
@@ -410,9 +411,8 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
 // ------------------------------------------------------------------------------------------
 // Backward: for image b accumulate  G[n,:] = sum_{(p,t)->n} a_bpt * (w_p*mu_p - w_p*xhat_n)
 //   a_bpt = gl[b,c,t] * pi_p * v[b,p,t] / exp(logits[b,c,t])      (wrong-class levels fold onto t = 0)
-// One CTA per (image, D-chunk).  Non-zero entries are compacted in a fixed order into a
-// shared-memory list; warp w owns rows n with (n & 7) == w and walks the list, so the
-// accumulation is atomics-free and deterministic.
+// One CTA per (image, D-chunk); see head_bwd_kernel below for the schedule (compaction, stable sort by patch row,
+// balanced walk, direct row writes) -- atomics-free and deterministic.
 __global__ void proto_weight_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
                                     float* __restrict__ w, float* __restrict__ wm, float* __restrict__ wsc,
                                     int* __restrict__ noniso, size_t n, int D) {

@@ -44,6 +44,13 @@ def _worker(rank, world, port, out):
     t, r, g = parallel.all_gather_mined(top1, rows, gt)
     ok &= t.flatten().tolist() == list(range(B * K)) and g.tolist() == list(range(B))
     ok &= r.flatten().tolist() == [float(i) for i in range(B * K * D)]
+    # the packed record bit-casts int32 / int64 fields through fp32 slots: patterns that are NaN / Inf as floats
+    # (labels -1, indices 0x7fc00000) must come back unchanged
+    gt2 = torch.full((b1 - b0,), -1, dtype=torch.int64)
+    top2 = torch.full((b1 - b0, K), 0x7fc00000, dtype=torch.int32)
+    t2, r2, g2 = parallel.all_gather_mined(top2, rows, gt2)
+    ok &= bool((g2 == -1).all()) and bool((t2 == 0x7fc00000).all()) and g2.numel() == B and t2.shape == (B, K)
+    ok &= r2.shape == (B, K, D) and t2.dtype == torch.int32 and g2.dtype == torch.int64
     # 3. sharded EM statistics, all-reduced == full-bank statistics
     rng = np.random.default_rng(0)
     Kc, Dd = 4, 8

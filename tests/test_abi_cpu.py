@@ -112,3 +112,15 @@ def test_memory_bank_cpu_bookkeeping():
             np.testing.assert_array_equal(lin[c, :ob.mem_len[c]], ob.data[c, :ob.mem_len[c]])
     data, labels = mb.pull_all()
     assert data.shape[0] == int(mb.mem_len.sum()) and labels.tolist() == sorted(labels.tolist())
+
+
+def test_header_constants_match_binding():
+    """#define MGP_* values in include/mgproto_b200.h == the Python mirror in _lib.py (layouts, math modes, errors)."""
+    import re
+    from mgproto_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mgproto_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(MGP_[A-Z0-9_]+)\s+(-?\d+)\b", hdr)}
+    for name in ("MGP_OUT_LOGP_NP", "MGP_OUT_LOGP_BPHW", "MGP_OUT_NEGP_BPHW", "MGP_OUT_TOP1_BP", "MGP_MATH_FP32",
+                 "MGP_MATH_TC", "MGP_MATH_AUTO", "MGP_MATH_TC_REUSE", "MGP_MATH_TC_ISO"):
+        assert name in defs, name
+        assert getattr(_lib, name) == defs[name], name

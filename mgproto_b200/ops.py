@@ -224,7 +224,10 @@ class HeadFunction(torch.autograd.Function):
         sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
         wt = weight_cp.detach().contiguous()
         xhat, inv, _ = normalize_fwd(x_add)
-        best = logprob_top1(xhat, mu, sg, B, HW, math) if (gt is not None and T <= min(32, HW)) else None
+        # the labelled fast path needs the tensor-core kernel and head_top1_kernel's shared-memory layout to fit
+        top1_smem = (2 * C * K + K * T + K * (HW + 1) + 2 * K * D + 2 * K + 4) * 4
+        use_top1 = gt is not None and T <= min(32, HW) and HW <= 1024 and top1_smem <= 200 * 1024
+        best = logprob_top1(xhat, mu, sg, B, HW, math) if use_top1 else None
         if best is not None:
             # labelled step: log p never reaches HBM (wrong-class prototypes only need their max, ref model.py:218-221)
             logits, vals, idx = head_select_top1(best, xhat, mu, sg, wt, _req(gt, torch.int64, "gt"), T, C, K, HW)
@@ -269,7 +272,8 @@ def head_level0(x_add, mu_ckd, sigma_ckd, weight_cp, math="auto"):
         sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
         wt = weight_cp.detach().contiguous()
         xhat, _, _ = normalize_fwd(x_add.detach().contiguous())
-        best = logprob_top1(xhat, mu, sg, B, HW, math)
+        fits = HW <= 1024 and (2 * C * K + 2 * K + K * (HW + 1) + 2 * K * D + 2 * K + 4) * 4 <= 200 * 1024
+        best = logprob_top1(xhat, mu, sg, B, HW, math) if fits else None
         if best is None:
             lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)
             return head_select(lp, wt, None, 1, C, K)[0][:, :, 0]

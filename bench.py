@@ -411,6 +411,28 @@ def main():
                                       "achieved": eb / t_em / 1e9, "peak": peak, "unit": "GB/s",
                                       "frac": eb / t_em / 1e9 / peak, "us_per_launch": t_em * 1e6,
                                       "note": "bank (82 MB) fits in L2 across repeats: upper-bound figure"}
+        # the largest kernel of the step: the whole update_GMM (em_plan + one cluster launch), all classes active
+        try:
+            Lp = int(getattr(net, "num_em_loop", 3))
+            for _ in range(3):
+                net.queue.updated.fill_(1)
+                net.update_GMM()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                net.queue.updated.fill_(1)
+                net.update_GMM()
+            e1.record()
+            torch.cuda.synchronize()
+            t_ug = e0.elapsed_time(e1) / reps / 1e3
+            ub = Lp * eb
+            extra["roofline_step_update_gmm"] = {
+                "kernel": "update_GMM = em_plan + em_fused_kernel (200 active classes, %d EM loops; + one fill)" % Lp,
+                "bound": "hbm", "achieved": ub / t_ug / 1e9, "peak": peak, "unit": "GB/s", "frac": ub / t_ug / 1e9 / peak,
+                "us_per_call": t_ug * 1e6, "algorithmic_bytes": ub,
+                "note": "issue/barrier-bound (DESIGN.md 5.3): bank rows re-read per EM loop, L2-resident after the first"}
+        except Exception as ex:  # noqa: BLE001 -- an auxiliary figure must never cost the bench line
+            extra["roofline_step_update_gmm"] = {"error": str(ex)[:200]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -359,7 +359,10 @@ def main():
                 "peak": peak, "unit": "GB/s", "frac": abytes / t_ka / 1e9 / peak, "traffic": traffic,
                 "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst: kernel timed alone)",
                 "us_per_launch": t_ka * 1e6, "algorithmic_bytes": abytes,
-                "pairs_per_sec": N * P / t_ka, "tensor_tflops_equiv": 4.0 * N * P * D / t_ka / 1e12}
+                "pairs_per_sec": N * P / t_ka, "tensor_tflops_equiv": 4.0 * N * P * D / t_ka / 1e12,
+                "note": "north-star kernel K-A (compute_log_prob / eval / push: log p materialised), timed alone; the "
+                        "labelled training step runs the max/arg-max variant instead (roofline_step_logprob) and its "
+                        "largest kernel is update_GMM (roofline_step_update_gmm)"}
         extra["roofline_logprob_op"] = {"kernel": "mgp_logprob_fwd [N,P] (%s): operand prep (fp16 hi/lo split of x and "
                                         "prototypes) + GEMM kernel" % args.math, "bound": "hbm",
                                         "achieved": abytes / t_op / 1e9, "peak": peak, "unit": "GB/s",

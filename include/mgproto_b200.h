@@ -58,6 +58,11 @@ int mgp_abi_version(void);
 const char* mgp_error_string(int code);
 /* 1 if the library was built with the sm_100a tcgen05 kernels */
 int mgp_has_tensor_core_path(void);
+/* Process-wide test / diagnosis switches (not part of the reference surface; the defaults are the product path).
+ * key "em_fused": 1 (default; 0 if MGP_EM_UNFUSED is set in the environment) = mgp_update_gmm runs the single
+ * cluster launch where the shape allows, 0 = always the multi-launch path (identical arithmetic, used by the
+ * parity tests to cross-check the two).  Returns the previous value, or MGP_ERR_INVALID for an unknown key. */
+int mgp_set_option(const char* key, int value);
 
 /* ---- a1  l2_normalize + rearrange -------------------------------------------------------
  * ref: model.py:40-41, :210-211, :431-432.
@@ -202,6 +207,8 @@ int mgp_em_update(const float* stats, int n_split, int with_s2, int n_rows_total
  * phase 1), phase 2 -- 3 + 2*num_em_loop launches enqueued on `stream`, nothing read back.  order [C] int32,
  * sched [2] int32 and stats [C][n_split][mgp_em_stat_stride(K,D,0)] fp32 are scratch.  (A batch-sharded
  * multi-GPU caller uses the individual entry points, with an all-reduce of stats between the two.) */
+/* number of kernel launches mgp_update_gmm enqueues for this shape (2 = planner + single cluster launch) */
+int mgp_update_gmm_launches(int K, int D, int cap, int num_em_loop);
 int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t* mem_len, float* mu,
                    const float* sigma, float* weight_cp, float* exp_avg, float* exp_avg_sq,
                    int32_t* adam_step, int32_t* order, int32_t* sched, float* stats, int n_split,

@@ -21,6 +21,7 @@ SIGNATURES = {
     "mgp_abi_version": (_i, []),
     "mgp_error_string": (C.c_char_p, [_i]),
     "mgp_has_tensor_core_path": (_i, []),
+    "mgp_set_option": (_i, [C.c_char_p, _i]),
     "mgp_normalize_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_normalize_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_logprob_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
@@ -34,6 +35,7 @@ SIGNATURES = {
     "mgp_bank_enqueue": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
     "mgp_bank_linearize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_stat_stride": (_sz, [_i, _i, _i]),
+    "mgp_update_gmm_launches": (_i, [_i, _i, _i, _i]),
     "mgp_update_gmm": (_i, [_vp] * 12 + [_i, _i] + [_f] * 7 + [_i] * 4 + [_vp]),
     "mgp_em_plan": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mgp_em_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),

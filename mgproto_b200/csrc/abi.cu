@@ -1,5 +1,7 @@
 // C-ABI glue: version / error strings and the log-likelihood dispatcher.
 #include "mgp_common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 int mgp_logprob_simt_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log,
                             float* out, int layout, int B, int HW, int P, int D, float* ws, cudaStream_t st);
@@ -22,6 +24,21 @@ extern "C" const char* mgp_error_string(int code) {
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "mgproto_b200: unknown error";
+}
+
+int g_mgp_em_fused = -1;   // -1: not decided yet (environment), see mgp_opt_em_fused()
+int mgp_opt_em_fused() {
+    if (g_mgp_em_fused < 0) g_mgp_em_fused = getenv("MGP_EM_UNFUSED") ? 0 : 1;
+    return g_mgp_em_fused;
+}
+extern "C" int mgp_set_option(const char* key, int value) {
+    if (!key) return MGP_ERR_INVALID;
+    if (strcmp(key, "em_fused") == 0) {
+        const int prev = mgp_opt_em_fused();
+        g_mgp_em_fused = value ? 1 : 0;
+        return prev;
+    }
+    return MGP_ERR_INVALID;
 }
 
 extern "C" int mgp_has_tensor_core_path(void) {

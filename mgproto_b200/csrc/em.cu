@@ -22,6 +22,8 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
+int mgp_opt_em_fused();   // abi.cu
+
 namespace {
 
 constexpr float EM_EPS = 1e-10f;
@@ -1407,6 +1409,14 @@ extern "C" int mgp_em_update(const float* stats, int n_split, int with_s2, int n
     return MGP_OK;
 }
 
+static bool em_fused_applies(int K, int D, int cap) {
+    return mgp_opt_em_fused() && K >= 2 && K <= 16 && (D == 64 || D == 128) && cap >= 2;
+}
+
+extern "C" int mgp_update_gmm_launches(int K, int D, int cap, int num_em_loop) {
+    return em_fused_applies(K, D, cap) ? 2 : 3 + 2 * num_em_loop;
+}
+
 extern "C" int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t* mem_len, float* mu, const float* sigma,
                               float* weight_cp, float* exp_avg, float* exp_avg_sq, int32_t* adam_step, int32_t* order,
                               int32_t* sched, float* stats, int n_split, int num_em_loop, float alpha, float lr,
@@ -1417,8 +1427,7 @@ extern "C" int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t
         return MGP_ERR_INVALID;
     int rc = mgp_em_plan(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop, stream);
     if (rc != MGP_OK) return rc;
-    static const bool unfused = (getenv("MGP_EM_UNFUSED") != nullptr);
-    if (!unfused && K >= 2 && K <= 16 && (D == 64 || D == 128) && cap >= 2) {
+    if (em_fused_applies(K, D, cap)) {
         // one cluster of two CTAs per class runs the class's whole timeline (em_fused_kernel)
         const int kh = (K + 1) / 2 <= 3 ? 3 : ((K + 1) / 2 <= 5 ? 5 : 8);
         const int per = (cap + 1) / 2;

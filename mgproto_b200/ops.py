@@ -377,8 +377,7 @@ def update_gmm(bank, updated, mem_len, mu_ckd, sigma_ckd, weight_cp, exp_avg, ex
                                      adam_step.data_ptr(), order.data_ptr(), sched.data_ptr(), stats.data_ptr(),
                                      int(n_split), int(num_em_loop), float(alpha), float(lr), float(beta1), float(beta2),
                                      float(adam_eps), float(tau), float(lamda), C, K, D, cap, _stream()), "mgp_update_gmm")
-    fused = 2 <= K <= 16 and D in (64, 128) and cap >= 2 and os.environ.get("MGP_EM_UNFUSED") is None
-    _count(2 if fused else 3 + 2 * int(num_em_loop))
+    _count(int(_lib.load().mgp_update_gmm_launches(K, D, cap, int(num_em_loop))))
 
 
 def em_estep(x_nd, mu_kd, sigma_kd, pi_k, want_log_resp=True, want_score=True):

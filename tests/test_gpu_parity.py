@@ -168,12 +168,13 @@ def test_head_backward_golden(golden, math):
         np.testing.assert_allclose(x.grad.cpu().numpy(), ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("math", ["fp32", "auto"])
 @pytest.mark.parametrize("em_path", ["fused", "generic"])
-def test_training_sequence_bank_and_em(golden, em_path):
+def test_training_sequence_bank_and_em(golden, em_path, math):
     """forward -> enqueue -> update_GMM over the fixture's iterations: bank contents, mem_len,
     update flags, mu, pi and the Adam state follow the reference step for step (KA7 included)."""
     g = golden
-    net = _model_from(g, "fp32")
+    net = _model_from(g, math)
     C, K, D, cap = (int(g[k]) for k in "C K D cap".split())
     if em_path == "generic":
         class AdamSub(torch.optim.Adam):      # not `type is Adam` -> host-driven generic path

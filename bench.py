@@ -20,7 +20,13 @@ The backbone is outside the path and is not timed.
           against MEASURED_PEAKS.json's HBM copy bandwidth (burst figure: kernel timed alone);
           roofline_step_logprob: the variant the labelled step runs (max/arg-max epilogue, log p stays on
           chip) against the measured dense bf16 tensor peak
-  cpu_baseline  the oracle port of the reference algorithm on the host cores, bounded sample
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, tools/install_reference.py) on the host cores, bounded
+          sample; the numpy oracle port only if baseline/_ref is absent
+  reference_gpu_eager  the same-box GPU bar: the unmodified reference model.py run eagerly on cuda:0 at the same
+          shapes (no_grad forward, train forward+backward, update_GMM), timed beside our stages
+
+Timing: the --steps block is repeated R >= 10 times (each bracketed by CUDA events); `value` uses the MEDIAN block,
+min/max are reported in `timing`.
 """
 from __future__ import annotations
 
@@ -102,28 +108,194 @@ def cpu_reference_step(n_img, seed=0, with_em=True, threads=1):
     return time.perf_counter() - t0
 
 
+
+# ------------------------------------------------------------------------------------------ the real reference
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, "model.py"))
+
+
+def _import_reference(cpu):
+    """Import the unmodified reference model.py from baseline/_ref.  On the CPU arm `Tensor.cuda` becomes a no-op
+    (model.py:391 hard-codes .cuda()); no reference file is touched."""
+    import importlib
+    import torch
+    if cpu:
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    return importlib.import_module("model")
+
+
+def synthetic_state(seed_mu=2, seed_bank=6):
+    """mu [C,K,D] and full bank rows [C,cap,D], shared by our model and the reference legs."""
+    import torch
+    import torch.nn.functional as F
+    c = CFG
+    mu = F.normalize(torch.rand(c["C"], c["K"], c["D"], generator=torch.Generator().manual_seed(seed_mu)), p=2, dim=2)
+    g6 = torch.Generator().manual_seed(seed_bank)
+    kk = torch.randint(0, c["K"], (c["C"], c["cap"]), generator=g6)
+    rows = mu[torch.arange(c["C"])[:, None], kk] + 0.3 * torch.randn(c["C"], c["cap"], c["D"], generator=g6)
+    return mu, F.normalize(rows, p=2, dim=2)
+
+
+def build_reference_model(ref, dev):
+    """The reference's MGProto (its own constructor) with the same synthetic mixture / full bank as build_model."""
+    import torch
+    import torch.nn as nn
+    c = CFG
+
+    class RESStub(nn.Module):                      # model.py:107-115 wants a backbone whose repr starts with "RES"
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(3, 16, kernel_size=1)
+
+        def forward(self, x):
+            return self.conv(x)
+
+    m = ref.MGProto(features=RESStub(), img_size=224, prototype_shape=(c["C"] * c["K"], c["D"], 1, 1),
+                    proto_layer_rf_info=None, num_classes=c["C"], init_weights=True,
+                    prototype_activation_function="log", add_on_layers_type="regular", sz_embedding=32,
+                    mem_capacity=c["cap"], mine_K=c["T"])
+    mu, rows = synthetic_state()
+    m.prototype_means.data.copy_(mu)
+    for i in range(c["C"]):
+        getattr(m.queue, "cls%d" % i).copy_(rows[i])
+    m.queue.mem_len.fill_(c["cap"])
+    m = m.to(dev)
+    m.prototype_optimizer = torch.optim.Adam([{"params": m.prototype_means, "lr": 3e-3}])
+    m.train()
+    return m
+
+
+def reference_step(m, x_add, gt, with_em=True):
+    """One hot-path step through the reference's own methods: forward (from the add-on features on: the backbone is
+    outside the path, so conv_features is pointed at the precomputed feature batch), the training loss of
+    train_and_test.py:37-45, backward to the features, update_GMM (train_and_test.py:61-63)."""
+    import torch
+    import torch.nn.functional as F
+    x_leaf = x_add.detach().clone().requires_grad_(True)
+    emb = torch.zeros(x_add.shape[0], 32, device=x_add.device)
+    m.conv_features = lambda _x: (x_leaf, emb)
+    out, _ = m(None, gt)
+    mine = sum(F.cross_entropy(out[:, :, k], gt) for k in range(1, out.shape[2])) / (out.shape[2] - 1)
+    loss = F.cross_entropy(out[:, :, 0], gt) + 0.2 * mine
+    loss.backward()
+    if with_em and m.queue.mem_len.sum() > 0:
+        m.update_GMM()
+    return out
+
+
+def cpu_reference_real(n_img, steps, warmup, threads):
+    """The unmodified reference on the host cores: `steps` timed steps of `n_img` images each -> mean seconds/step."""
+    import torch
+    torch.set_num_threads(threads)
+    ref = _import_reference(cpu=True)
+    m = build_reference_model(ref, torch.device("cpu"))
+    c = CFG
+    gen = torch.Generator().manual_seed(1)
+    ts = []
+    for i in range(warmup + steps):
+        x = torch.randn(n_img, c["D"], c["H"], c["W"], generator=gen)
+        gt = torch.randint(0, c["C"], (n_img,), generator=gen)
+        t0 = time.perf_counter()
+        reference_step(m, x, gt)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            ts.append(dt)
+        elif dt > 40.0:                       # a slow host: the warm-up step is the sample (keeps the run bounded)
+            return dt
+    return statistics.mean(ts)
+
+
+def reference_gpu_eager(dev, feats, gts, ours):
+    """the same-box GPU bar -- the unmodified reference run eagerly on the B200 at the bench
+    shapes, stage by stage, beside our own stages (`ours`: dict of callables).  CUDA events, 1 warm-up + 3 timed."""
+    import torch
+    ref = _import_reference(cpu=False)
+    m = build_reference_model(ref, dev)
+    c = CFG
+    res = {"what": "unmodified reference model.py (baseline/_ref) on cuda:0, eager ATen/cuBLAS kernels, same synthetic "
+                   "mixture, bank and feature batches; conv_features points at the precomputed add-on features"}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    emb = torch.zeros(c["B"], 32, device=dev)
+    x, gt = feats[0], gts[0]
+
+    def ref_fwd_nograd():
+        with torch.no_grad():
+            m.conv_features = lambda _x: (x, emb)
+            m(None, None)
+
+    def ref_train():
+        reference_step(m, x, gt, with_em=False)
+
+    def ref_em():
+        m.memory_updated_cls[:] = False
+        m.memory_updated_cls[torch.unique(gt).cpu()] = True
+        m.update_GMM()
+
+    stages = (("forward_nograd", ref_fwd_nograd), ("train_fwd_bwd_enqueue", ref_train), ("update_GMM", ref_em))
+    for name, fn in stages:
+        try:
+            t_ref = timed(fn)
+            t_ours = timed(ours[name], n=10, warm=2)
+            res[name] = {"reference_ms": t_ref, "ours_ms": t_ours, "speedup": t_ref / t_ours}
+        except Exception as ex:  # noqa: BLE001 -- e.g. out of memory in the reference's [N/4,P,D] temporaries
+            res[name] = {"error": str(ex)[:160]}
+            torch.cuda.empty_cache()
+    res["active_classes_update_GMM"] = int(torch.unique(gt).numel())
+    del m
+    torch.cuda.empty_cache()
+    return res
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     th = _cpu_threads()
-    n_img = max(2, th)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_step(n_img, threads=th)
-    ts = [cpu_reference_step(n_img, seed=s, threads=th) for s in range(max(1, min(args.steps, 5)))]
-    t = statistics.mean(ts)
-    val = n_img / t
     c = CFG
+    if reference_available():
+        # the unmodified reference (torch CPU, all host threads): 8 images per step keeps a step at ~10-20 s
+        # (torch's CPU kernels stop scaling -- and at 128 threads get 10x slower -- on these small ATen ops: 16 threads)
+        th = min(os.cpu_count() or 1, 16)
+        n_img, steps = 8, max(1, min(args.steps, 2))
+        t = cpu_reference_real(n_img, steps, warmup=1, threads=th)
+        kind = "reference"
+        sample = ("%d images of the 256-image batch per step x %d steps, full 200x10x128 mixture and 800-row banks: "
+                  "unmodified reference model.py (baseline/_ref) forward from the add-on features + loss + backward + "
+                  "enqueue + update_GMM of the touched classes, torch CPU on %d threads" % (n_img, steps, th))
+    else:
+        n_img = max(2, th)
+        for _ in range(max(1, min(args.warmup, 1))):
+            cpu_reference_step(n_img, threads=th)
+        ts = [cpu_reference_step(n_img, seed=s, threads=th) for s in range(max(1, min(args.steps, 5)))]
+        t, steps, kind = statistics.mean(ts), len(ts), "port"
+        sample = ("%d images of the 256-image batch per step, full 200x10x128 mixture, forward + enqueue + update_GMM of "
+                  "the touched classes; numpy oracle port, head on %d threads (baseline/_ref absent)" % (n_img, th))
+    val = n_img / t
     line = {
         "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": len(ts), "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": _config(args.gpus),
         "pairs_per_sec": val * c["H"] * c["W"] * c["C"] * c["K"],
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": th, "kind": "port",
-                         "sample": "%d images of the 256-image batch per step, full 200x10x128 mixture, forward + "
-                                   "enqueue + update_GMM of the touched classes; numpy oracle port, head on %d threads "
-                                   "(the Python reference cannot travel to the GPU box)" % (n_img, th)},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": th, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -131,10 +303,13 @@ def run_reference_arm(args):
 
 def _config(n_gpus):
     c = CFG
-    return {"workload": "BASELINE.json configs[1]: batch %d/GPU add-on feature maps [%d,%d,%d,%d], %dx%dx%d diag-Gaussian "
-                        "mixture, T=%d, bank %d rows/class; step = head fwd+bwd + enqueue + update_GMM"
+    par = "single GPU" if n_gpus == 1 else ("dp%d: images sharded, prototypes/bank replicated; one all-gather of the mined "
+                                            "rows per step, update_GMM replicated on every rank (no EM collective)" % n_gpus)
+    return {"workload": "head-only, pre-computed add-on features (backbone outside the path): BASELINE.json configs[1] "
+                        "shapes, batch %d/GPU feature maps [%d,%d,%d,%d], %dx%dx%d diag-Gaussian mixture, T=%d, bank %d "
+                        "rows/class; step = head fwd+bwd + enqueue + update_GMM"
                         % (c["B"], c["B"], c["D"], c["H"], c["W"], c["C"], c["K"], c["D"], c["T"], c["cap"]),
-            "global_batch": c["B"] * n_gpus, "parallelism": "dp%d (image-sharded, EM stats all-reduce)" % n_gpus,
+            "global_batch": c["B"] * n_gpus, "parallelism": par,
             "l2": "inputs rotate through %d distinct batches (%.0f MB) > 126 MB L2; the labelled step keeps log p on chip (no [B,P,HW] intermediate)"
                   % (N_ROT, N_ROT * c["B"] * c["D"] * c["H"] * c["W"] * 4 / 1e6)}
 
@@ -189,14 +364,10 @@ def build_model(dev, seed=0):
     net = M.MGProto(features=nn.Sequential(nn.Conv2d(3, 8, 1)), img_size=224, prototype_shape=(c["C"] * c["K"], c["D"], 1, 1),
                     proto_layer_rf_info=None, num_classes=c["C"], add_on_layers_type="regular", sz_embedding=32,
                     mem_capacity=c["cap"], mine_K=c["T"])
-    mu = M.l2_normalize(torch.rand(c["C"], c["K"], c["D"], generator=torch.Generator().manual_seed(2)), dim=2)
+    mu, rows = synthetic_state()
     net.prototype_means.data.copy_(mu)
     net = net.to(dev)
-    # every class's bank full: rows = l2_normalize(mu_ck + 0.3 randn)
-    g6 = torch.Generator().manual_seed(6)
-    kk = torch.randint(0, c["K"], (c["C"], c["cap"]), generator=g6)
-    rows = mu[torch.arange(c["C"])[:, None], kk] + 0.3 * torch.randn(c["C"], c["cap"], c["D"], generator=g6)
-    net.queue.bank.copy_(M.l2_normalize(rows, dim=2).to(dev))
+    net.queue.bank.copy_(rows.to(dev))                    # every class's bank full
     net.queue.mem_len.fill_(c["cap"])
     net.prototype_optimizer = torch.optim.Adam([{"params": net.prototype_means, "lr": 3e-3}])
     net.train()
@@ -218,6 +389,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference_gpu_eager leg")
+    ap.add_argument("--reps", type=int, default=10, help="repetitions of the --steps block (median reported)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -269,23 +442,32 @@ def main():
     for i in range(W):
         step(feats[i % N_ROT], gts[i % N_ROT])
     barrier()
-    l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    R = max(10, args.reps)                        # the --steps block is repeated R times; value = median block
+    blocks = []
     barrier()
     t_w0 = time.time()
-    e0.record()
-    for i in range(args.steps):
-        step(feats[i % N_ROT], gts[i % N_ROT])
-    e1.record()
-    barrier()
+    launches = 0
+    for r in range(R):
+        l0 = ops.launch_count()
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(feats[(r * args.steps + i) % N_ROT], gts[(r * args.steps + i) % N_ROT])
+        e1.record()
+        barrier()
+        tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        blocks.append(float(tm))
+        launches = ops.launch_count() - l0
     t_w1 = time.time()
-    ms = e0.elapsed_time(e1)
-    launches = ops.launch_count() - l0
-    tm = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms = float(tm)
+    ms = statistics.median(blocks)
     value = B * world * args.steps / (ms / 1e3)
+    timing = {"reps": R, "block_ms_median": ms, "block_ms_min": min(blocks), "block_ms_max": max(blocks),
+              "value_from": "median block of %d x %d steps, max over ranks per block" % (R, args.steps),
+              "images_per_s_min": B * world * args.steps / (max(blocks) / 1e3),
+              "images_per_s_max": B * world * args.steps / (min(blocks) / 1e3)}
 
     # ---- end to end: host buffers in, logits out ---------------------------------------------
     # every step copies its own pinned-host feature batch to the device and reads its logits back to pinned host
@@ -306,15 +488,19 @@ def main():
         sink.wait()
 
     e2e_run(3)
-    barrier()
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * args.steps / (float(tm) / 1e3)
+    e2e_blocks = []
+    for _ in range(5):
+        barrier()
+        e0.record()
+        e2e_run(args.steps)
+        e1.record()
+        barrier()
+        tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_blocks.append(float(tm))
+    e2e_val = B * world * args.steps / (statistics.median(e2e_blocks) / 1e3)
+    timing["e2e_block_ms"] = {"median": statistics.median(e2e_blocks), "min": min(e2e_blocks), "max": max(e2e_blocks)}
     clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
 
     # ---- roofline of the log-likelihood kernel (timed alone, rank 0) --------------------------
@@ -439,13 +625,52 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        th = _cpu_threads()
-        n_img = max(2, th)
-        cpu_reference_step(n_img, threads=th)
-        ts = [cpu_reference_step(n_img, seed=s, threads=th) for s in range(3)]
-        cpu = {"value": n_img / statistics.mean(ts), "unit": "images/s", "cores": th, "kind": "port",
-               "sample": "%d images/step x 3 steps of the same workload (forward + enqueue + update_GMM of the touched "
-                         "classes), numpy oracle port of the reference algorithm, head on %d threads" % (n_img, th)}
+        if reference_available():
+            # the unmodified reference on the host cores, in a child process without GPUs (its `.cuda()` shim and
+            # its thread pool stay out of this one)
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+                env.pop(k, None)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                    "--warmup", "1"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                   timeout=600)
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception as ex:  # noqa: BLE001
+                cpu = {"error": str(ex)[:200]}
+        if cpu is None or "error" in cpu:
+            th = _cpu_threads()
+            n_img = max(2, th)
+            cpu_reference_step(n_img, threads=th)
+            ts = [cpu_reference_step(n_img, seed=s, threads=th) for s in range(3)]
+            cpu = {"value": n_img / statistics.mean(ts), "unit": "images/s", "cores": th, "kind": "port",
+                   "sample": "%d images/step x 3 steps of the same workload (forward + enqueue + update_GMM of the touched "
+                             "classes), numpy oracle port of the reference algorithm, head on %d threads" % (n_img, th)}
+
+    # ---- the same-box GPU bar: the unmodified reference, eager, on this GPU (rank 0, N = 1) -----------------
+    if rank == 0 and world == 1 and not args.no_ref_gpu and reference_available():
+        try:
+            def ours_fwd():
+                with torch.no_grad():
+                    net.head(feats[0], None)
+
+            def ours_train():
+                x = feats[0]
+                x.grad = None
+                x.requires_grad_(True)
+                out = net.head(x, gts[0])
+                loss_fn(out, gts[0]).backward()
+                x.requires_grad_(False)
+
+            def ours_em():
+                net.queue.updated.zero_()
+                net.queue.updated[torch.unique(gts[0])] = 1
+                net.update_GMM()
+
+            extra["reference_gpu_eager"] = reference_gpu_eager(
+                dev, feats, gts, {"forward_nograd": ours_fwd, "train_fwd_bwd_enqueue": ours_train, "update_GMM": ours_em})
+        except Exception as ex:  # noqa: BLE001
+            extra["reference_gpu_eager"] = {"error": str(ex)[:200]}
 
     if rank == 0:
         line = {
@@ -456,7 +681,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * D * HW * 4,
                     "d2h_bytes_per_step": B * c["C"] * c["T"] * 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "math": args.math,
+            "math": args.math, "timing": timing,
         }
         line.update(extra)
         print(json.dumps(line))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MGP_ABI_VERSION 1
+#define MGP_ABI_VERSION 2   /* 2: Adam hyper-parameters and tau travel as double (see mgp_em_update) */
 
 #define MGP_OK 0
 #define MGP_ERR_INVALID (-1)      /* null pointer / non-positive size / misalignment      */
@@ -59,6 +59,7 @@ const char* mgp_error_string(int code);
 /* 1 if the library was built with the sm_100a tcgen05 kernels */
 int mgp_has_tensor_core_path(void);
 /* Process-wide test / diagnosis switches (not part of the reference surface; the defaults are the product path).
+ * key "em_tc": 1 (default; 0 if MGP_EM_NO_TC is set) = mgp_update_gmm may take the tensor-core kernel;
  * key "em_fused": 1 (default; 0 if MGP_EM_UNFUSED is set in the environment) = mgp_update_gmm runs the single
  * cluster launch where the shape allows, 0 = always the multi-launch path (identical arithmetic, used by the
  * parity tests to cross-check the two).  Returns the previous value, or MGP_ERR_INVALID for an unknown key. */
@@ -152,9 +153,16 @@ int mgp_head_bwd(const float* grad_logits, const float* logits, const float* val
  * plan [B*K] int32 is scratch.  gt outside [0,C) skips the image. */
 int mgp_mined_gather(const float* xhat_nd, const int32_t* idx, const int64_t* gt, int32_t* top1,
                      float* rows, int B, int HW, int C, int K, int D, int T, void* stream);
+/* shadow_h / shadow_l [C,cap,D] fp16 and shadow_xx [C,cap] fp32 (all three or none): the tensor-core operand copy of
+ * the bank -- hi / lo halves of 256 * row and |row|^2 -- kept in step by the scatter (see mgp_update_gmm). */
 int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, uint8_t* updated,
                      const float* rows, const int32_t* top1, const int64_t* gt, int32_t* plan,
+                     void* shadow_h, void* shadow_l, float* shadow_xx,
                      int B, int C, int K, int D, int cap, void* stream);
+/* (Re)builds the whole shadow from the fp32 bank: after the bank was written by anything but mgp_bank_enqueue
+ * (checkpoint load, MemoryBank.push, direct tensor writes). */
+int mgp_bank_shadow_sync(const float* bank, void* shadow_h, void* shadow_l, float* shadow_xx, int C, int cap, int D,
+                         void* stream);
 
 /* Copies the ring of every class into oldest->newest order: lin [C,cap,D] (rows >= mem_len
  * zero).  This is the layout of the reference's queue.cls%d buffers (state_dict wire format). */
@@ -195,11 +203,14 @@ int mgp_em_plan(uint8_t* updated, const int64_t* mem_len, int32_t* order, int32_
 int mgp_em_stats(const float* bank, const int32_t* order, const float* mu, const float* sigma,
                  const float* weight_cp, float alpha, int row_begin, int row_end, int n_split,
                  int with_s2, float* stats, int C, int K, int D, int cap, void* stream);
+/* lr, beta1, beta2, adam_eps and tau are DOUBLES: torch.optim.Adam and momentum_update (model.py:44-50) hold them as
+ * Python floats and form 1 - beta / 1 - tau in double before narrowing to fp32; a float parameter would bake
+ * 1.0f - 0.999f (1.3e-5 off) into exp_avg_sq. */
 int mgp_em_update(const float* stats, int n_split, int with_s2, int n_rows_total,
                   const int32_t* order, const int32_t* sched, float* mu, const float* sigma,
                   float* weight_cp, float* exp_avg, float* exp_avg_sq, int em_loop,
-                  int num_em_loop, int phase, float lr, float beta1, float beta2, float adam_eps,
-                  float tau, float lamda, float* grad_out, int only_class, int C, int K, int D,
+                  int num_em_loop, int phase, double lr, double beta1, double beta2, double adam_eps,
+                  double tau, float lamda, float* grad_out, int only_class, int C, int K, int D,
                   void* stream);
 
 /* The whole update_GMM (ref model.py:277-301) of a single-GPU replica in one call: mgp_em_plan (with the
@@ -207,13 +218,20 @@ int mgp_em_update(const float* stats, int n_split, int with_s2, int n_rows_total
  * phase 1), phase 2 -- 3 + 2*num_em_loop launches enqueued on `stream`, nothing read back.  order [C] int32,
  * sched [2] int32 and stats [C][n_split][mgp_em_stat_stride(K,D,0)] fp32 are scratch.  (A batch-sharded
  * multi-GPU caller uses the individual entry points, with an all-reduce of stats between the two.) */
-/* number of kernel launches mgp_update_gmm enqueues for this shape (2 = planner + single cluster launch) */
-int mgp_update_gmm_launches(int K, int D, int cap, int num_em_loop);
-int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t* mem_len, float* mu,
+/* With the bank's shadow (shadow_h / shadow_l / shadow_xx, see mgp_bank_enqueue; may be NULL) and sigma_iso != 0 --
+ * the caller's assertion that sigma is constant over d inside every prototype, which holds for every state the
+ * reference's training loop reaches -- shapes K <= 16, D in {128, 256} run as ONE tensor-core launch after the planner
+ * (csrc/em_tc.cu: both inner products as tcgen05 GEMMs on fp16 hi/lo splits).  The kernel re-checks sigma and sets
+ * status[0] = 1 (leaving that class untouched) if the assertion was wrong.  Otherwise: K <= 16, D in {64, 128}: one
+ * fp32 cluster launch; any other shape: the launches listed above. */
+/* number of kernel launches mgp_update_gmm enqueues for this shape (2 = planner + single launch) */
+int mgp_update_gmm_launches(int K, int D, int cap, int num_em_loop, int have_shadow_iso);
+int mgp_update_gmm(const float* bank, const void* shadow_h, const void* shadow_l, const float* shadow_xx,
+                   int sigma_iso, int32_t* status, uint8_t* updated, const int64_t* mem_len, float* mu,
                    const float* sigma, float* weight_cp, float* exp_avg, float* exp_avg_sq,
                    int32_t* adam_step, int32_t* order, int32_t* sched, float* stats, int n_split,
-                   int num_em_loop, float alpha, float lr, float beta1, float beta2, float adam_eps,
-                   float tau, float lamda, int C, int K, int D, int cap, void* stream);
+                   int num_em_loop, float alpha, double lr, double beta1, double beta2, double adam_eps,
+                   double tau, float lamda, int C, int K, int D, int cap, void* stream);
 
 /* ---- a11/a13/a14  EM building blocks on explicit rows ---------------------------------------
  * ref: model.py:303-321 (_e_step), :338-365 (_m_step), :403-421 (_score).

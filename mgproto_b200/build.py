@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgproto_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["abi.cu", "normalize.cu", "logprob_simt.cu", "logprob_tc.cu", "head.cu", "bank.cu", "em.cu"]
+SOURCES = ["abi.cu", "normalize.cu", "logprob_simt.cu", "logprob_tc.cu", "head.cu", "bank.cu", "em.cu", "em_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DMGP_WITH_TC"]
 
@@ -46,19 +46,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
+    # per-object stamps: an object is recompiled when its source, any header or the flags changed
+    hdr = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + ["../../include/mgproto_b200.h"]:
+        if f.endswith((".cuh", ".h")):
+            hdr.update(open(os.path.join(CSRC, f), "rb").read())
+    hdr.update(" ".join(NVCC_FLAGS).encode())
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+        h = hdr.copy()
+        h.update(open(os.path.join(CSRC, src), "rb").read())
+        odig = h.hexdigest()
+        if os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read().strip() == odig:
+            continue
+        cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, obj, odig, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
-    for src, p in procs:
+    for src, obj, odig, p in procs:
         out, _ = p.communicate()
         log.append("== %s\n%s" % (src, out))
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as fh:
-        fh.write("\n".join(log))
+        with open(obj + ".stamp", "w") as fh:
+            fh.write(odig)
+        with open(os.path.join(HERE, "build", src.replace(".cu", ".ptxas.log")), "w") as fh:
+            fh.write(out)
     if verbose:
         print("\n".join(log))
     cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]

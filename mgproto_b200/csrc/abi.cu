@@ -31,8 +31,18 @@ int mgp_opt_em_fused() {
     if (g_mgp_em_fused < 0) g_mgp_em_fused = getenv("MGP_EM_UNFUSED") ? 0 : 1;
     return g_mgp_em_fused;
 }
+int g_mgp_em_tc = -1;
+int mgp_opt_em_tc() {
+    if (g_mgp_em_tc < 0) g_mgp_em_tc = getenv("MGP_EM_NO_TC") ? 0 : 1;
+    return g_mgp_em_tc;
+}
 extern "C" int mgp_set_option(const char* key, int value) {
     if (!key) return MGP_ERR_INVALID;
+    if (strcmp(key, "em_tc") == 0) {
+        const int prev = mgp_opt_em_tc();
+        g_mgp_em_tc = value ? 1 : 0;
+        return prev;
+    }
     if (strcmp(key, "em_fused") == 0) {
         const int prev = mgp_opt_em_fused();
         g_mgp_em_fused = value ? 1 : 0;

@@ -8,9 +8,42 @@
 // no host synchronisation: a single-CTA planner (dedupe, per-class offsets, ring arithmetic)
 // and a row scatter.  Row order inside a class does not change any EM result except through
 // fp32 summation order; mgp_bank_linearize reproduces the reference layout on demand.
+#include <cuda_fp16.h>
+
 #include "mgp_common.cuh"
 
 namespace {
+
+// fp16 hi / lo split of 256 x (22 mantissa bits; the factor keeps the lo part in fp16's normal range for unit-norm
+// rows) + |x|^2: the tensor-core EM kernel (em_tc.cu) TMA-loads these tiles instead of converting fp32 rows on chip.
+__device__ __forceinline__ void shadow_store_row(const float* __restrict__ src, __half* __restrict__ xh,
+                                                 __half* __restrict__ xl, float* __restrict__ xx, size_t row, int D,
+                                                 int lane) {
+    float ss = 0.f;
+    for (int d4 = lane; d4 < D / 4; d4 += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(src + 4 * d4);
+        const float a[4] = {v.x, v.y, v.z, v.w};
+        __align__(8) __half h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ss = fmaf(a[i], a[i], ss);
+            const float s1 = a[i] * 256.0f;
+            h[i] = __float2half_rn(s1);
+            l[i] = __float2half_rn(s1 - __half2float(h[i]));
+        }
+        *reinterpret_cast<uint2*>(xh + row * D + 4 * d4) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(xl + row * D + 4 * d4) = *reinterpret_cast<uint2*>(l);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) xx[row] = ss;
+}
+
+__global__ void bank_shadow_kernel(const float* __restrict__ bank, __half* __restrict__ xh, __half* __restrict__ xl,
+                                   float* __restrict__ xx, long long rows, int D) {
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wg >= rows) return;
+    shadow_store_row(bank + (size_t)wg * D, xh, xl, xx, (size_t)wg, D, threadIdx.x & 31);
+}
 
 __global__ void __launch_bounds__(1024)
 enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, uint8_t* __restrict__ updated,
@@ -180,8 +213,9 @@ __global__ void mined_gather_kernel(const float* __restrict__ xhat, const int32_
 }
 
 __global__ void enqueue_scatter_kernel(float* __restrict__ bank, const float* __restrict__ rows,
-                                       const int64_t* __restrict__ gt, const int32_t* __restrict__ plan, int B, int K,
-                                       int D, int cap) {
+                                       const int64_t* __restrict__ gt, const int32_t* __restrict__ plan,
+                                       __half* __restrict__ xh, __half* __restrict__ xl, float* __restrict__ xx, int B,
+                                       int K, int D, int cap) {
     const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (wg >= B * K) return;
@@ -191,6 +225,7 @@ __global__ void enqueue_scatter_kernel(float* __restrict__ bank, const float* __
     const float4* src = reinterpret_cast<const float4*>(rows + (size_t)wg * D);
     float4* dst = reinterpret_cast<float4*>(bank + ((size_t)c * cap + slot) * D);
     for (int d = lane; d < D / 4; d += 32) dst[d] = src[d];
+    if (xh) shadow_store_row(rows + (size_t)wg * D, xh, xl, xx, (size_t)c * cap + slot, D, lane);   // keep the shadow in step
 }
 
 __global__ void bank_linearize_kernel(const float* __restrict__ bank, const int64_t* __restrict__ mem_len,
@@ -222,9 +257,10 @@ extern "C" int mgp_mined_gather(const float* xhat_nd, const int32_t* idx, const 
 }
 
 extern "C" int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, uint8_t* updated, const float* rows,
-                                const int32_t* top1, const int64_t* gt, int32_t* plan, int B, int C, int K, int D,
-                                int cap, void* stream) {
+                                const int32_t* top1, const int64_t* gt, int32_t* plan, void* shadow_h, void* shadow_l,
+                                float* shadow_xx, int B, int C, int K, int D, int cap, void* stream) {
     if (!bank || !mem_len || !head || !updated || !rows || !top1 || !gt || !plan) return MGP_ERR_INVALID;
+    if ((shadow_h != nullptr) != (shadow_l != nullptr) || (shadow_h != nullptr) != (shadow_xx != nullptr)) return MGP_ERR_INVALID;
     if (B <= 0 || C <= 0 || K <= 0 || D <= 0 || cap <= 0 || (D & 3)) return MGP_ERR_INVALID;
     if (B > 8192 || K > 64) return MGP_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -233,7 +269,18 @@ extern "C" int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, ui
     enqueue_plan_kernel<<<1, 1024, smem, st>>>(mem_len, head, updated, top1, gt, plan, B, C, K, cap);
     MGP_CHECK_LAUNCH();
     const int warps = B * K;
-    enqueue_scatter_kernel<<<(warps + 7) / 8, 256, 0, st>>>(bank, rows, gt, plan, B, K, D, cap);
+    enqueue_scatter_kernel<<<(warps + 7) / 8, 256, 0, st>>>(bank, rows, gt, plan, reinterpret_cast<__half*>(shadow_h),
+                                                            reinterpret_cast<__half*>(shadow_l), shadow_xx, B, K, D, cap);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}
+
+extern "C" int mgp_bank_shadow_sync(const float* bank, void* shadow_h, void* shadow_l, float* shadow_xx, int C, int cap,
+                                    int D, void* stream) {
+    if (!bank || !shadow_h || !shadow_l || !shadow_xx || C <= 0 || cap <= 0 || D <= 0 || (D & 3)) return MGP_ERR_INVALID;
+    const long long rows = (long long)C * cap;
+    bank_shadow_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        bank, reinterpret_cast<__half*>(shadow_h), reinterpret_cast<__half*>(shadow_l), shadow_xx, rows, D);
     MGP_CHECK_LAUNCH();
     return MGP_OK;
 }

@@ -19,14 +19,21 @@
 // (class, loop) step also decays the momentum of -- and moves -- all other classes.
 // Classes only interact through the global step count, so each class replays its own timeline.
 #include "mgp_common.cuh"
+#include "em_common.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
 int mgp_opt_em_fused();   // abi.cu
+int mgp_opt_em_tc();      // abi.cu
+// em_tc.cu
+bool mgp_em_tc_supported(int K, int D, int cap);
+int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* shadow_xx, const int32_t* order,
+                     const int32_t* sched, float* mu, const float* sigma, float* weight, float* exp_avg, float* exp_avg_sq,
+                     int* status, int num_em_loop, float alpha, double lr, double beta1, double beta2, double adam_eps,
+                     double tau, float lamda, int C, int K, int D, int cap, cudaStream_t st);
 
 namespace {
 
-constexpr float EM_EPS = 1e-10f;
 
 __global__ void __launch_bounds__(1024)
 em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_len, int32_t* __restrict__ order,
@@ -639,22 +646,6 @@ em_stats_fast_kernel(const float* __restrict__ bank, const int32_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-struct AdamCfg {
-    float lr, beta1, beta2, eps;
-};
-
-__device__ __forceinline__ void adam_apply(float& p, float& m, float& v, float g, const AdamCfg& a, double b1pow,
-                                           double b2pow) {
-    // torch.optim.Adam (_single_tensor_adam): lerp, mul/addcmul, bias corrections in double
-    m = m + (g - m) * (1.0f - a.beta1);
-    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
-    const float step_size = (float)((double)a.lr / (1.0 - b1pow));
-    const float bc2_sqrt = (float)sqrt(1.0 - b2pow);
-    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
-    p = p - step_size * (m / denom);
-}
-
-// ---------------------------------------------------------------------------------------------
 // The whole update_GMM of a single replica in ONE launch (after em_plan): classes only interact through the global
 // Adam step count (file header), so a cluster of two CTAs owns a class for all of its timeline --
 //   leading zero-gradient steps, num_em_loop x [E-step + statistics over the class's bank rows (each CTA half of
@@ -668,7 +659,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 3)
 em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ order, const int32_t* __restrict__ sched,
                 float* __restrict__ mu, const float* __restrict__ sigma, float* __restrict__ weight,
                 float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float alpha, int rbf, int num_em_loop,
-                AdamCfg adam, float tau, float lamda, int C, int K, int cap) {
+                AdamCfg adam, float tau, float omtau, float lamda, int C, int K, int cap) {
     constexpr int DP = D + 4, K2 = 2 * KH, RS = (K2 + 3) & ~3, G = 256 / D, D4 = D / 4, TAB = 256;
     constexpr int NE = (K2 * D + 255) / 256;                     // elements of the class's [K,D] state owned by a thread
     cg::cluster_group cluster = cg::this_cluster();
@@ -694,6 +685,7 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
     float* s_c = s_e + K2 * K2;          // [TAB]
     float* s_d = s_c + TAB;              // [TAB]
     __shared__ float s_adam[2];
+    __shared__ float s_tail[2];
     float* mu_c = mu + (size_t)c * KD;
     const float* sg_c = sigma + (size_t)c * KD;
 
@@ -714,34 +706,34 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
         float a_[NE];
 #pragma unroll
         for (int i = 0; i < NE; ++i) a_[i] = sqrtf(v_[i]);
-        int cutoff = count;
-        if (adam.beta1 > 0.f && adam.beta1 < 1.f) cutoff = (int)ceilf(logf(1e-6f) / logf(adam.beta1));
-        const int count_p = min(count, max(cutoff, 1));
+        const int count_p = replay_explicit_steps(count, first, (float)adam.beta1);
         for (int s0 = 0; s0 < count_p; s0 += TAB) {
             const int ns = min(TAB, count_p - s0);
             __syncthreads();
-            for (int s = tid; s < ns; s += 256) {
-                const double st = (double)(s0 + s + 1);
-                const double l1 = log((double)adam.beta1), l2 = log((double)adam.beta2);
-                const double b1s = exp(st * l1), b2s = exp(st * l2);
-                const double b1t = exp(((double)first + st) * l1);
-                const double b2t = exp(((double)first + st) * l2);
-                s_c[s] = (float)((double)adam.lr * b1s / (1.0 - b1t));
-                s_d[s] = (float)(sqrt(b2s) / sqrt(1.0 - b2t));
-            }
+            for (int s = tid; s < ns; s += 256) replay_coeffs(adam, first, s0 + s + 1, s_c[s], s_d[s]);
+            if (tid == 255 && s0 + TAB >= count_p && count > count_p) replay_tail(adam, first, count_p, count, s_tail[0], s_tail[1]);
             __syncthreads();
             for (int s = 0; s < ns; ++s) {
                 const float cs = -s_c[s], ds = s_d[s];
 #pragma unroll
                 for (int i = 0; i < NE; ++i) {
                     float rc;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.eps)));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.epsf)));
                     p_[i] = fmaf(cs * m_[i], rc, p_[i]);
                 }
             }
         }
-        const float mdec = (float)pow((double)adam.beta1, (double)count);
-        const float vdec = (float)pow((double)adam.beta2, (double)count);
+        if (count > count_p) {                       // steps count_p+1 .. count in one term (see replay_tail)
+            const float cs = -s_tail[0], ds = s_tail[1];
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                float rc;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.epsf)));
+                p_[i] = fmaf(cs * m_[i], rc, p_[i]);
+            }
+        }
+        const float mdec = (float)pow(adam.beta1, (double)count);
+        const float vdec = (float)pow(adam.beta2, (double)count);
 #pragma unroll
         for (int i = 0; i < NE; ++i) { m_[i] *= mdec; v_[i] *= vdec; }
     };
@@ -995,8 +987,8 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
         }
         if (tid == 0) {
             const double stp = (double)(step0 + L * ord + loop + 1);
-            s_adam[0] = (float)((double)adam.lr / (1.0 - pow((double)adam.beta1, stp)));
-            s_adam[1] = (float)sqrt(1.0 - pow((double)adam.beta2, stp));
+            s_adam[0] = (float)(adam.lr / (1.0 - pow(adam.beta1, stp)));
+            s_adam[1] = (float)sqrt(1.0 - pow(adam.beta2, stp));
         }
         cluster.sync();                                           // the partner has read my partials; s_s0 / s_e / s_adam visible
         // Adam's bias corrections of this step (torch: double), computed once per CTA
@@ -1020,9 +1012,9 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
             }
             g += div_scale * (esum * muv - emu);
             // torch.optim.Adam (_single_tensor_adam): lerp, mul/addcmul
-            const float mm = m_[i] + (g - m_[i]) * (1.0f - adam.beta1);
-            const float vv = v_[i] * adam.beta2 + (1.0f - adam.beta2) * g * g;
-            const float denom = sqrtf(vv) / bc2_sqrt + adam.eps;
+            const float mm = m_[i] + (g - m_[i]) * adam.omb1;
+            const float vv = v_[i] * adam.b2f + adam.omb2 * g * g;
+            const float denom = sqrtf(vv) / bc2_sqrt + adam.epsf;
             newp[i] = muv - step_size * (mm / denom);
             m_[i] = mm; v_[i] = vv;
         }
@@ -1033,7 +1025,7 @@ em_fused_kernel(const float* __restrict__ bank, const int32_t* __restrict__ orde
             p_[i] = newp[i];
             if (o < KD) s_mu[o] = newp[i];
         }
-        if (tid < K) s_pi[tid] = tau * s_pi[tid] + (1.0f - tau) * ((s_s0[tid] + EM_EPS) / n_rows);   // ref :385, :399
+        if (tid < K) s_pi[tid] = tau * s_pi[tid] + omtau * ((s_s0[tid] + EM_EPS) / n_rows);   // ref :385, :399
         __syncthreads();
     }
     replay(step0 + L * (ord + 1), L * (n_active - ord - 1));
@@ -1049,7 +1041,7 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
                  const int32_t* __restrict__ order, const int32_t* __restrict__ sched, float* __restrict__ mu,
                  const float* __restrict__ sigma, float* __restrict__ weight, float* __restrict__ exp_avg,
                  float* __restrict__ exp_avg_sq, int em_loop, int num_em_loop, int phase, AdamCfg adam, float tau,
-                 float lamda, float* __restrict__ grad_out, int only_class, int C, int K, int D) {
+                 float omtau, float lamda, float* __restrict__ grad_out, int only_class, int C, int K, int D) {
     const int c = blockIdx.x;
     const int ord = order[c];
     const int n_active = sched[0];
@@ -1092,24 +1084,16 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
                     a_[i] = sqrtf(exp_avg_sq[(size_t)c * KD + o]);
                 }
             }
-            // the s-th term carries beta1^s: with beta1 = 0.9 the terms after step 128 are < 1.4e-6 of the first
-            // and add < 1e-7 (absolute) to a parameter that moves by <= 10*lr in total -- below fp32 resolution of
-            // the sum -- so the parameter update stops at beta1^s < 1e-6; the moments still decay by `count`
-            int cutoff = count;
-            if (adam.beta1 > 0.f && adam.beta1 < 1.f) cutoff = (int)ceilf(logf(1e-6f) / logf(adam.beta1));
-            const int count_p = min(count, max(cutoff, 1));
+            // explicit terms up to beta1^s < 1e-3, the rest as one geometric tail term (replay_explicit_steps /
+            // replay_tail above); the moments decay by the full `count`
+            const int count_p = replay_explicit_steps(count, first, (float)adam.beta1);
+            __shared__ float s_tail[2];
             for (int s0 = 0; s0 < count_p; s0 += TAB) {
                 const int ns = min(TAB, count_p - s0);
                 __syncthreads();
-                for (int s = tid; s < ns; s += 256) {
-                    const double st = (double)(s0 + s + 1);
-                    const double l1 = log((double)adam.beta1), l2 = log((double)adam.beta2);
-                    const double b1s = exp(st * l1), b2s = exp(st * l2);
-                    const double b1t = exp(((double)first + st) * l1);
-                    const double b2t = exp(((double)first + st) * l2);
-                    s_c[s] = (float)((double)adam.lr * b1s / (1.0 - b1t));
-                    s_d[s] = (float)(sqrt(b2s) / sqrt(1.0 - b2t));
-                }
+                for (int s = tid; s < ns; s += 256) replay_coeffs(adam, first, s0 + s + 1, s_c[s], s_d[s]);
+                if (tid == 255 && s0 + TAB >= count_p && count > count_p)
+                    replay_tail(adam, first, count_p, count, s_tail[0], s_tail[1]);
                 __syncthreads();
                 const int nel = min(8, (KD - ob + 255) / 256);         // elements this thread row actually owns
                 // one FMA + one MUFU.RCP + FMUL + FMA per (step, element); the element count is a compile-time
@@ -1119,7 +1103,7 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
         const float cs = -s_c[s], ds = s_d[s];                                                                      \
         _Pragma("unroll") for (int i = 0; i < NEL; ++i) {                                                           \
             float rc;                                                                                               \
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.eps)));                          \
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.epsf)));                          \
             p_[i] = fmaf(cs * m0_[i], rc, p_[i]);                                                                   \
         }                                                                                                           \
     }
@@ -1128,8 +1112,17 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
                 else { MGP_REPLAY(8) }
 #undef MGP_REPLAY
             }
-            const float mdec = (float)pow((double)adam.beta1, (double)count);
-            const float vdec = (float)pow((double)adam.beta2, (double)count);
+            if (count > count_p) {                   // steps count_p+1 .. count in one term (see replay_tail)
+                const float cs = -s_tail[0], ds = s_tail[1];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float rc;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[i], ds, adam.epsf)));
+                    p_[i] = fmaf(cs * m0_[i], rc, p_[i]);
+                }
+            }
+            const float mdec = (float)pow(adam.beta1, (double)count);
+            const float vdec = (float)pow(adam.beta2, (double)count);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int o = ob + tid + 256 * i;
@@ -1172,7 +1165,7 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
     const float n_rows = (float)n_rows_total;
     const float div_scale = -4.0f * lamda / ((float)K * (float)(K - 1));
     const int step = step0 + num_em_loop * ord + em_loop + 1;
-    const double b1p = pow((double)adam.beta1, (double)step), b2p = pow((double)adam.beta2, (double)step);
+    const double b1p = pow(adam.beta1, (double)step), b2p = pow(adam.beta2, (double)step);
     // all global operands of up to 8 owned elements are fetched before any is used (the kernel is a chain of
     // cold-miss latencies otherwise: ncu long_scoreboard 5.6 per issue)
     for (int ob = 0; ob < KD; ob += 256 * 8) {
@@ -1220,7 +1213,7 @@ em_update_kernel(const float* __restrict__ stats, int n_split, size_t stat_strid
     for (int k = tid; k < K; k += 256) {
         float* wp = weight + (size_t)c * P + (size_t)c * K + k;
         const float pi_new = (s_s0[k] + EM_EPS) / n_rows;
-        *wp = tau * (*wp) + (1.0f - tau) * pi_new;
+        *wp = tau * (*wp) + omtau * pi_new;
     }
 }
 
@@ -1388,8 +1381,8 @@ extern "C" int mgp_em_stats(const float* bank, const int32_t* order, const float
 
 extern "C" int mgp_em_update(const float* stats, int n_split, int with_s2, int n_rows_total, const int32_t* order,
                              const int32_t* sched, float* mu, const float* sigma, float* weight_cp, float* exp_avg,
-                             float* exp_avg_sq, int em_loop, int num_em_loop, int phase, float lr, float beta1,
-                             float beta2, float adam_eps, float tau, float lamda, float* grad_out, int only_class,
+                             float* exp_avg_sq, int em_loop, int num_em_loop, int phase, double lr, double beta1,
+                             double beta2, double adam_eps, double tau, float lamda, float* grad_out, int only_class,
                              int C, int K, int D, void* stream) {
     if (!order || !sched || !mu || !sigma || !weight_cp) return MGP_ERR_INVALID;
     if (phase < 0 || phase > 2 || C <= 0 || K <= 0 || D <= 0 || num_em_loop <= 0) return MGP_ERR_INVALID;
@@ -1400,10 +1393,10 @@ extern "C" int mgp_em_update(const float* stats, int n_split, int with_s2, int n
     if (smem < 2 * 2048 * sizeof(float)) smem = 2 * 2048 * sizeof(float);
     if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
     MGP_CUDA(cudaFuncSetAttribute(em_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AdamCfg a{lr, beta1, beta2, adam_eps};
+    const AdamCfg a = make_adam(lr, beta1, beta2, adam_eps);
     em_update_kernel<<<C, 256, smem, (cudaStream_t)stream>>>(stats, n_split, stride, n_rows_total, order, sched, mu,
                                                              sigma, weight_cp, exp_avg, exp_avg_sq, em_loop,
-                                                             num_em_loop, phase, a, tau, lamda, grad_out, only_class,
+                                                             num_em_loop, phase, a, (float)tau, (float)(1.0 - tau), lamda, grad_out, only_class,
                                                              C, K, D);
     MGP_CHECK_LAUNCH();
     return MGP_OK;
@@ -1413,20 +1406,49 @@ static bool em_fused_applies(int K, int D, int cap) {
     return mgp_opt_em_fused() && K >= 2 && K <= 16 && (D == 64 || D == 128) && cap >= 2;
 }
 
-extern "C" int mgp_update_gmm_launches(int K, int D, int cap, int num_em_loop) {
+static bool em_tc_applies(int K, int D, int cap, int have_shadow_iso) {
+#ifdef MGP_WITH_TC
+    return have_shadow_iso && mgp_opt_em_tc() && mgp_em_tc_supported(K, D, cap);
+#else
+    (void)K; (void)D; (void)cap; (void)have_shadow_iso;
+    return false;
+#endif
+}
+
+extern "C" int mgp_update_gmm_launches(int K, int D, int cap, int num_em_loop, int have_shadow_iso) {
+    if (em_tc_applies(K, D, cap, have_shadow_iso)) return 2;
     return em_fused_applies(K, D, cap) ? 2 : 3 + 2 * num_em_loop;
 }
 
-extern "C" int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t* mem_len, float* mu, const float* sigma,
+// shape / resource validation shared by the paths below: nothing is enqueued (and no flag cleared, no step counted)
+// for a shape the kernels cannot take
+static int em_validate(int C, int K, int D, int cap, int num_em_loop) {
+    if (C <= 0 || K <= 0 || D <= 0 || cap <= 0 || num_em_loop <= 0) return MGP_ERR_INVALID;
+    if (K > 64 || (D % 4) != 0 || D > 512) return MGP_ERR_UNSUPPORTED;
+    if (((size_t)2 * K * D + (size_t)RB * D + (size_t)RB * K + 2 * K) * sizeof(float) > 220 * 1024) return MGP_ERR_UNSUPPORTED;
+    return MGP_OK;
+}
+
+extern "C" int mgp_update_gmm(const float* bank, const void* shadow_h, const void* shadow_l, const float* shadow_xx,
+                              int sigma_iso, int32_t* status, uint8_t* updated, const int64_t* mem_len, float* mu,
+                              const float* sigma,
                               float* weight_cp, float* exp_avg, float* exp_avg_sq, int32_t* adam_step, int32_t* order,
-                              int32_t* sched, float* stats, int n_split, int num_em_loop, float alpha, float lr,
-                              float beta1, float beta2, float adam_eps, float tau, float lamda, int C, int K, int D,
+                              int32_t* sched, float* stats, int n_split, int num_em_loop, float alpha, double lr,
+                              double beta1, double beta2, double adam_eps, double tau, float lamda, int C, int K, int D,
                               int cap, void* stream) {
     if (!bank || !updated || !mem_len || !mu || !sigma || !weight_cp || !exp_avg || !exp_avg_sq || !adam_step ||
         !order || !sched || !stats)
         return MGP_ERR_INVALID;
-    int rc = mgp_em_plan(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop, stream);
+    int rc = em_validate(C, K, D, cap, num_em_loop);                 // before the planner clears flags / counts steps
     if (rc != MGP_OK) return rc;
+    rc = mgp_em_plan(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop, stream);
+    if (rc != MGP_OK) return rc;
+#ifdef MGP_WITH_TC
+    if (shadow_h && shadow_l && shadow_xx && status && em_tc_applies(K, D, cap, sigma_iso))
+        return mgp_em_tc_launch(shadow_h, shadow_l, shadow_xx, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq,
+                                status, num_em_loop, alpha, lr, beta1, beta2, adam_eps, tau, lamda, C, K, D, cap,
+                                (cudaStream_t)stream);
+#endif
     if (em_fused_applies(K, D, cap)) {
         // one cluster of two CTAs per class runs the class's whole timeline (em_fused_kernel)
         const int kh = (K + 1) / 2 <= 3 ? 3 : ((K + 1) / 2 <= 5 ? 5 : 8);
@@ -1439,13 +1461,13 @@ extern "C" int mgp_update_gmm(const float* bank, uint8_t* updated, const int64_t
         if (rbf * dp > xfl) xfl = rbf * dp;
         const size_t fsmem = ((size_t)2 * k2 * dp + xfl + (size_t)rbf * rs + (size_t)k2 * D + 13 * k2 + (size_t)k2 * k2 + 512) *
                              sizeof(float);
-        AdamCfg a{lr, beta1, beta2, adam_eps};
+        const AdamCfg a = make_adam(lr, beta1, beta2, adam_eps);
         cudaStream_t fst = (cudaStream_t)stream;
 #define MGP_EM_FUSED(DD, KK)                                                                                        \
     if (D == DD && kh == KK) {                                                                                      \
         MGP_CUDA(cudaFuncSetAttribute(em_fused_kernel<DD, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
         em_fused_kernel<DD, KK><<<2 * C, 256, fsmem, fst>>>(bank, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq, \
-                                                            alpha, rbf, num_em_loop, a, tau, lamda, C, K, cap);     \
+                                                            alpha, rbf, num_em_loop, a, (float)tau, (float)(1.0 - tau), lamda, C, K, cap);     \
         MGP_CHECK_LAUNCH();                                                                                         \
         return MGP_OK;                                                                                              \
     }

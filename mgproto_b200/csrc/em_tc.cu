@@ -1,0 +1,460 @@
+// a10-a12 on the 5th-gen tensor cores: the whole update_GMM (ref model.py:277-301, :303-321, :367-401) of a single
+// replica in ONE launch after em_plan, one CTA per class, for the shapes the shipped loop produces
+// (K <= 16 components, D = 128 or 256, sigma constant over d inside every component).
+//
+// Per class and EM loop the two inner products are GEMMs over the class's bank rows X [cap x D]:
+//     E-step     Q  [cap x K]  = X . A^T        A_k = -2 w_k mu_k          (q_nk = w_k (|x_n|^2 + |mu_k|^2) + Q_nk)
+//     statistics S1^T [D x K]  = X^T . R        R_nk = smoothed responsibility
+// They run as tcgen05.mma (kind::f16, fp32 accumulators in TMEM) on fp16 hi/lo splits -- hi*hi + lo*hi + hi*lo, 22
+// mantissa bits, the scheme of logprob_tc.cu -- of
+//   * the bank rows: a SHADOW of the fp32 bank kept in HBM as fp16 hi / lo of 256 x (written by the enqueue scatter,
+//     csrc/bank.cu), so a 128-row tile is four TMA boxes into 128B-swizzled shared memory with no conversion pass.
+//     The same tile serves both GEMMs: as the K-major A operand of the E-step (rows x d) and as the MN-major A operand
+//     of the statistics GEMM (d x rows) -- one copy, two descriptors;
+//   * the means operand A (rebuilt from the on-chip means after every Adam step) and the responsibilities R (written
+//     by the E-step epilogue), both split in registers and stored in the UMMA K-major SWIZZLE_128B layout.
+// Everything else (soft-max, S0, gradient, diversity term, Adam, pi momentum, the zero-gradient replay of the other
+// classes' steps) is fp32 SIMT on the class's state, which stays in registers / shared memory for the whole timeline
+// exactly as in em_fused_kernel (em.cu); thread d owns mean / moment elements (k, d) for all k.
+//
+// Pipeline per 128-row tile: TMA load (mbarrier) -> 3*D/16 E-step MMAs -> epilogue (tcgen05.ld, soft-max, R) ->
+// 3*D/16 statistics MMAs accumulating in TMEM across the tiles of the loop.  One tile buffer per CTA; two CTAs per SM
+// (D = 128) overlap each other's latencies.  HBM/L2 traffic: num_em_loop x (4 D + 4) bytes per bank row -- the
+// algorithmic bytes of SURVEY 8(d) K-D.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "mgp_common.cuh"
+#include "em_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace mgp_em;
+using namespace mgp_tc;
+
+constexpr float SX = 256.0f;      // shadow rows hold 256 x (fp16 hi + lo)
+constexpr float SR = 1024.0f;     // responsibilities are stored as 1024 r
+constexpr int TR = 128;           // bank rows per tile (UMMA M of the E-step, K extent of the statistics GEMM)
+constexpr int NK = 16;            // UMMA N: components padded to 16
+constexpr int TAB = 256;
+
+struct EmTcParams {
+    const float* xx;              // [C*cap] |x|^2 of the bank rows (shadow)
+    const int32_t* order;
+    const int32_t* sched;
+    float* mu;
+    const float* sigma;
+    float* weight;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int* status;                  // set to 1 if a class turned out to have anisotropic sigma (its update is skipped)
+    AdamCfg adam;
+    float alpha, tau, omtau, lamda;
+    int num_em_loop, C, K, cap;
+};
+
+// byte offset of element (row r < 16, col k) of a [16 x D] fp16 operand stored K-major SWIZZLE_128B as D/64 blocks of
+// [16 rows x 128 B]: 16-byte chunks XOR-ed with (row & 7)
+__device__ __forceinline__ uint32_t swz16(int r, int k) {
+    return (uint32_t)((k >> 6) * 2048 + r * 128 + (((((k & 63) >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+template <int D, int KT>
+__global__ void __launch_bounds__(256, (D == 128) ? 2 : 1)
+em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const EmTcParams prm) {
+    constexpr int NCH = D / 64;                    // 64-element (128 B) chunks along d
+    constexpr uint32_t CH_BYTES = TR * 128;        // one [128 rows x 64] fp16 block
+    constexpr uint32_t X_BYTES = NCH * CH_BYTES;   // hi (lo follows)
+    constexpr int DB = D / 128;                    // 128-wide d blocks (statistics accumulators)
+    constexpr int OWN = D;                         // threads owning mean/moment elements: thread d <-> (k, d) for all k
+    constexpr int ISSUER = 128;                    // the TMA / MMA issuing thread: lane 0 of warp 4 (warps 0-3 run the E-step epilogue)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* bp = smem_raw + (base - raw);
+    // carve-up (bytes from `base`)
+    const uint32_t o_xh = 0, o_xl = X_BYTES;
+    const uint32_t o_ah = 2 * X_BYTES, o_al = o_ah + NCH * 2048;          // means operand [16 x D] hi / lo
+    const uint32_t o_rh = o_al + NCH * 2048, o_rl = o_rh + 4096;          // responsibilities [16 x 128 rows] hi / lo
+    const uint32_t o_mu = o_rl + 4096;                                    // fp32 means [KT][D]
+    const uint32_t o_misc = o_mu + KT * D * 4;
+    float* s_mu = reinterpret_cast<float*>(bp + o_mu);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bp + o_misc);            // tma, estep, stats (+ TMEM slot)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    float* s_e = reinterpret_cast<float*>(bars + 4);                      // [KT][KT]
+    float* s_c = s_e + KT * KT;                                           // [TAB]
+    float* s_d = s_c + TAB;                                               // [TAB]
+    float* s_red = s_d + TAB;                                             // [8][16]
+    float* s_w = s_red + 128;                                             // [16] w_k
+    float* s_ls = s_w + 16;                                               // [16] sum_d (log(sigma+eps) + log(2pi)/2)
+    float* s_pi = s_ls + 16;                                              // [16]
+    float* s_cst = s_pi + 16;                                             // [16]
+    float* s_s0 = s_cst + 16;                                             // [16]
+    float* s_misc = s_s0 + 16;                                            // [8]: tail c, tail d, adam step size, bc2 sqrt, scale
+    const uint32_t bar_tma = smem_u32(bars), bar_e = bar_tma + 8, bar_s = bar_tma + 16;
+
+    const int c = blockIdx.x;
+    const int ord = prm.order[c];
+    const int n_active = prm.sched[0], step0 = prm.sched[1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = prm.K, cap = prm.cap, L = prm.num_em_loop, P = prm.C * K, KD = K * D;
+    const AdamCfg& adam = prm.adam;
+    const bool own = tid < OWN;
+    float* mu_c = prm.mu + (size_t)c * KD;
+    const float* sg_c = prm.sigma + (size_t)c * KD;
+
+    float p_[KT], m_[KT], v_[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        p_[k] = 0.f; m_[k] = 0.f; v_[k] = 1.f;
+        if (own && k < K) {
+            const size_t o = (size_t)c * KD + k * D + tid;
+            p_[k] = prm.mu[o]; m_[k] = prm.exp_avg[o]; v_[k] = prm.exp_avg_sq[o];
+        }
+    }
+    // `count` zero-gradient Adam steps first+1 .. first+count on the registers (em_common.cuh)
+    auto replay = [&](int first, int count) {
+        if (count <= 0) return;
+        float a_[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) a_[k] = sqrtf(v_[k]);
+        const int count_p = replay_explicit_steps(count, first, (float)adam.beta1);
+        for (int s0 = 0; s0 < count_p; s0 += TAB) {
+            const int ns = min(TAB, count_p - s0);
+            __syncthreads();
+            for (int s = tid; s < ns; s += 256) replay_coeffs(adam, first, s0 + s + 1, s_c[s], s_d[s]);
+            if (tid == 255 && s0 + TAB >= count_p && count > count_p) replay_tail(adam, first, count_p, count, s_misc[0], s_misc[1]);
+            __syncthreads();
+            if (own) {
+                for (int s = 0; s < ns; ++s) {
+                    const float cs = -s_c[s], ds = s_d[s];
+#pragma unroll
+                    for (int k = 0; k < KT; ++k) {
+                        float rc;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[k], ds, adam.epsf)));
+                        p_[k] = fmaf(cs * m_[k], rc, p_[k]);
+                    }
+                }
+            }
+        }
+        if (count > count_p && own) {
+            const float cs = -s_misc[0], ds = s_misc[1];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                float rc;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[k], ds, adam.epsf)));
+                p_[k] = fmaf(cs * m_[k], rc, p_[k]);
+            }
+        }
+        const float mdec = (float)pow(adam.beta1, (double)count), vdec = (float)pow(adam.beta2, (double)count);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { m_[k] *= mdec; v_[k] *= vdec; }
+    };
+    auto write_back = [&]() {
+        if (!own) return;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+            if (k < K) {
+                const size_t o = (size_t)c * KD + k * D + tid;
+                prm.mu[o] = p_[k]; prm.exp_avg[o] = m_[k]; prm.exp_avg_sq[o] = v_[k];
+            }
+    };
+
+    if (ord < 0) {                                   // inactive class: it only takes everybody's zero-gradient steps
+        replay(step0, L * n_active);
+        write_back();
+        return;
+    }
+
+    // ---- set-up: barriers, TMEM, sigma-derived constants, zeroed operand tiles
+    if (tid == 0) {
+        mbar_init(bar_tma, 1);
+        mbar_init(bar_e, 1);
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    bool same = true;
+    for (int i = tid; i < KD; i += 256) same = same && (sg_c[i] == sg_c[(i / D) * D]);
+    for (uint32_t i = tid * 16u; i < 2u * NCH * 2048u + 8192u; i += 256u * 16u)        // A hi/lo and R hi/lo: rows >= K stay zero
+        *reinterpret_cast<uint4*>(bp + o_ah + i) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 16) {
+        float w = 0.f, ls = 0.f, pi = 0.f;
+        if (tid < K) {
+            const float sg = sg_c[tid * D] + EM_EPS;                                     // ref :333-334
+            w = 1.0f / (sg * sg);
+            ls = (float)D * (logf(sg) + 0.5f * MGP_LOG_2PI);                             // D equal terms
+            pi = prm.weight[(size_t)c * P + (size_t)c * K + tid];
+        }
+        s_w[tid] = w; s_ls[tid] = ls; s_pi[tid] = pi;
+    }
+    tc_fence_before();
+    const bool iso = __syncthreads_and(same ? 1 : 0) != 0;
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (!iso) {                                      // the host promised isotropic sigma: flag it, leave the class untouched
+        if (tid == 0) atomicExch(prm.status, 1);
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+        return;
+    }
+    replay(step0, L * ord);
+
+    const int ntiles = (cap + TR - 1) / TR;
+    const float n_rows = (float)cap;
+    const float inv_den = 1.0f / (1.0f + (float)K * prm.alpha);
+    const float div_scale = -4.0f * prm.lamda / ((float)K * (float)(K - 1));
+    const uint32_t idesc_e = umma_idesc_f16(TR, NK, 0, 0);          // E-step: A = X (K-major), B = means (K-major)
+    const uint32_t idesc_s = umma_idesc_f16(128, NK, 1, 0);         // statistics: A = X^T (MN-major), B = R (K-major)
+    const uint32_t d_e = tmem_base;                                  // [128 rows x 16]
+    const uint32_t d_s = tmem_base + 16;                             // DB x [128 d x 16]
+    uint32_t tile_ctr = 0;                                           // tiles issued so far (mbarrier phases)
+
+    for (int loop = 0; loop < L; ++loop) {
+        // ---- means operand, |mu_k|^2, diversity kernel from the current means
+        float amax = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+            if (own && k < K) {
+                s_mu[k * D + tid] = p_[k];
+                amax = fmaxf(amax, fabsf(2.0f * s_w[k] * p_[k]));
+            }
+        amax = warp_max(amax);
+        if (lane == 0) s_red[warp] = amax;
+        __syncthreads();
+        if (tid == 0) {
+            float mx = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, s_red[w8]);
+            int ex = 0;
+            if (mx > 0.f) frexpf(mx, &ex);
+            s_misc[4] = ldexpf(1.0f, 8 - ex);                        // max |a| * scale in [128, 256)
+        }
+        __syncthreads();
+        const float a_scale = s_misc[4];
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+            if (own && k < K) {
+                const float a = -2.0f * s_w[k] * p_[k] * a_scale;
+                const __half h = __float2half_rn(a);
+                const uint32_t off = swz16(k, tid);
+                *reinterpret_cast<__half*>(bp + o_ah + off) = h;
+                *reinterpret_cast<__half*>(bp + o_al + off) = __float2half_rn(a - __half2float(h));
+            }
+        for (int k = warp; k < K; k += 8) {                          // |mu_k|^2 and the per-component constant
+            float mm = 0.f;
+            for (int d = lane; d < D; d += 32) mm = fmaf(s_mu[k * D + d], s_mu[k * D + d], mm);
+            mm = warp_sum(mm);
+            if (lane == 0) s_cst[k] = -s_ls[k] + logf(s_pi[k] + EM_EPS) - 0.5f * s_w[k] * mm;   // ref :316, :323-336
+        }
+        for (int pr = warp; pr < K * K; pr += 8) {                   // ref utils/helpers.py:13-14, model.py:390-392
+            const int i = pr / K, j = pr - i * K;
+            float t = 0.f;
+            for (int d = lane; d < D; d += 32) {
+                const float df = s_mu[i * D + d] - s_mu[j * D + d];
+                t = fmaf(df, df, t);
+            }
+            t = warp_sum(t);
+            if (lane == 0) s_e[i * KT + j] = (i == j) ? 0.f : expf(-t);
+        }
+        if (tid == 0) {
+            const double stp = (double)(step0 + L * ord + loop + 1);
+            s_misc[2] = (float)(adam.lr / (1.0 - pow(adam.beta1, stp)));
+            s_misc[3] = (float)sqrt(1.0 - pow(adam.beta2, stp));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // operand stores -> visible to the MMA (async proxy)
+        __syncthreads();
+
+        float s0[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) s0[k] = 0.f;
+        const float inv_a = 1.0f / (a_scale * SX);
+
+        for (int t = 0; t < ntiles; ++t, ++tile_ctr) {
+            const uint32_t par = tile_ctr & 1u;
+            if (tid == ISSUER) {
+                if (tile_ctr > 0) mbar_wait(bar_s, (tile_ctr - 1) & 1u);     // previous statistics MMAs have read X and R
+                mbar_expect_tx(bar_tma, 2 * X_BYTES);
+                const int row0 = c * cap + t * TR;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    tma_load_2d(base + o_xh + ch * CH_BYTES, &map_h, ch * 64, row0, bar_tma);
+                    tma_load_2d(base + o_xl + ch * CH_BYTES, &map_l, ch * 64, row0, bar_tma);
+                }
+                mbar_wait(bar_tma, par);
+                tc_fence_after();
+                // E-step: D_e[row, k] = sum_d X[row, d] A[k, d]   (3 passes: hi.hi + lo.hi + hi.lo)
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks) {
+                    const uint32_t xo = (uint32_t)(ks >> 2) * CH_BYTES + (uint32_t)(ks & 3) * 32u;
+                    const uint32_t ao = (uint32_t)(ks >> 2) * 2048u + (uint32_t)(ks & 3) * 32u;
+                    const uint64_t xh = umma_desc(base + o_xh + xo), xl = umma_desc(base + o_xl + xo);
+                    const uint64_t ah = umma_desc(base + o_ah + ao), al = umma_desc(base + o_al + ao);
+                    tc_mma_f16(d_e, xh, ah, idesc_e, ks != 0);
+                    tc_mma_f16(d_e, xl, ah, idesc_e, 1u);
+                    tc_mma_f16(d_e, xh, al, idesc_e, 1u);
+                }
+                tc_commit(bar_e);
+            }
+            if (warp < 4) {
+                // ---- E-step epilogue: thread = bank row
+                const int row = t * TR + tid;
+                const bool valid = row < cap;
+                const float xxv = valid ? __ldg(prm.xx + (size_t)c * cap + row) : 0.f;
+                mbar_wait(bar_e, par);
+                tc_fence_after();
+                uint32_t q[16];
+                tmem_ld16(d_e + ((uint32_t)(warp * 32) << 16), q);
+                tmem_ld_wait();
+                float wl[KT], mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    const float qq = fmaf(s_w[k], xxv, __uint_as_float(q[k]) * inv_a);
+                    wl[k] = (k < K) ? s_cst[k] - 0.5f * qq : -INFINITY;                 // lp + log(pi + eps)  (ref :316)
+                    mx = fmaxf(mx, wl[k]);
+                }
+                float se = 0.f;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    wl[k] = (k < K) ? expf(wl[k] - mx) : 0.f;
+                    se += wl[k];
+                }
+                const float inv_se = 1.0f / se;
+                const uint32_t rbase = (uint32_t)(tid >> 6) * 2048u + (uint32_t)(tid & 7) * 2u;
+                const int c16 = (tid & 63) >> 3;
+#pragma unroll
+                for (int k = 0; k < KT; ++k)
+                    if (k < K) {
+                        const float r = valid ? fmaf(wl[k], inv_se, prm.alpha) * inv_den : 0.f;   // ref :380-383
+                        s0[k] += r;
+                        const float rs = r * SR;
+                        const __half h = __float2half_rn(rs);
+                        const uint32_t off = rbase + (uint32_t)k * 128u + (uint32_t)(((c16 ^ (k & 7)) & 7) << 4);
+                        *reinterpret_cast<__half*>(bp + o_rh + off) = h;
+                        *reinterpret_cast<__half*>(bp + o_rl + off) = __float2half_rn(rs - __half2float(h));
+                    }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tc_fence_before();
+            }
+            __syncthreads();
+            if (tid == ISSUER) {
+                tc_fence_after();
+                // statistics: D_s[d, k] += sum_row X[row, d] R[row, k]
+#pragma unroll
+                for (int db = 0; db < DB; ++db) {
+#pragma unroll
+                    for (int ks = 0; ks < TR / 16; ++ks) {
+                        const uint32_t xo = (uint32_t)db * 2u * CH_BYTES + (uint32_t)ks * 2048u;   // 16 rows x 128 B
+                        const uint32_t ro = (uint32_t)(ks >> 2) * 2048u + (uint32_t)(ks & 3) * 32u;
+                        const uint64_t xh = umma_desc_mn(base + o_xh + xo, CH_BYTES, 1024u);
+                        const uint64_t xl = umma_desc_mn(base + o_xl + xo, CH_BYTES, 1024u);
+                        const uint64_t rh = umma_desc(base + o_rh + ro), rl = umma_desc(base + o_rl + ro);
+                        tc_mma_f16(d_s + db * 16, xh, rh, idesc_s, (t | ks) != 0);
+                        tc_mma_f16(d_s + db * 16, xl, rh, idesc_s, 1u);
+                        tc_mma_f16(d_s + db * 16, xh, rl, idesc_s, 1u);
+                    }
+                }
+                tc_commit(bar_s);
+            }
+        }
+        // ---- S0 over the class, S1 from TMEM
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            float v = s0[k];
+            v = warp_sum(v);
+            if (lane == 0 && warp < 4) s_red[warp * 16 + k] = v;
+        }
+        mbar_wait(bar_s, (tile_ctr - 1) & 1u);                        // all statistics MMAs of this loop have retired
+        tc_fence_after();
+        __syncthreads();
+        if (tid < K) s_s0[tid] = (s_red[tid] + s_red[16 + tid]) + (s_red[32 + tid] + s_red[48 + tid]);
+        uint32_t sacc[16];
+        if (own) {
+            tmem_ld16(d_s + (uint32_t)(tid >> 7) * 16u + ((uint32_t)((warp & 3) * 32) << 16), sacc);
+            tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- gradient + diversity + Adam on the owned elements (ref model.py:385-397)
+        if (own) {
+            const float step_size = s_misc[2], bc2_sqrt = s_misc[3];
+#pragma unroll
+            for (int k = 0; k < KT; ++k)
+                if (k < K) {
+                    const float muv = p_[k];
+                    const float s1 = __uint_as_float(sacc[k]) * (1.0f / (SX * SR));
+                    float g = -(s1 - muv * s_s0[k]) * s_w[k] / n_rows;
+                    float esum = 0.f, emu = 0.f;
+                    for (int j = 0; j < K; ++j) {
+                        const float e = s_e[k * KT + j];
+                        esum += e;
+                        emu = fmaf(e, s_mu[j * D + tid], emu);
+                    }
+                    g += div_scale * (esum * muv - emu);
+                    const float mm = m_[k] + (g - m_[k]) * adam.omb1;             // torch.optim.Adam (_single_tensor_adam)
+                    const float vv = v_[k] * adam.b2f + adam.omb2 * g * g;
+                    const float denom = sqrtf(vv) / bc2_sqrt + adam.epsf;
+                    p_[k] = muv - step_size * (mm / denom);
+                    m_[k] = mm; v_[k] = vv;
+                }
+        }
+        __syncthreads();                                              // every reader of s_mu / s_s0 is done
+        if (tid < K) s_pi[tid] = prm.tau * s_pi[tid] + prm.omtau * ((s_s0[tid] + EM_EPS) / n_rows);   // ref :385, :399, :297
+    }
+    replay(step0 + L * (ord + 1), L * (n_active - ord - 1));
+    write_back();
+    if (tid < K) prm.weight[(size_t)c * P + (size_t)c * K + tid] = s_pi[tid];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+    }
+}
+
+template <int D>
+size_t em_tc_smem(int kt) {
+    return 1024 + 2 * (size_t)(D / 64) * TR * 128 + 2 * (size_t)(D / 64) * 2048 + 8192 + (size_t)kt * D * 4 +
+           ((size_t)kt * kt + 2 * TAB + 128 + 6 * 16 + 8) * 4 + 64;
+}
+
+}  // namespace
+
+bool mgp_em_tc_supported(int K, int D, int cap) {
+    return K >= 2 && K <= 16 && (D == 128 || D == 256) && cap >= 1 && get_encode() != nullptr;
+}
+
+int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* shadow_xx, const int32_t* order,
+                     const int32_t* sched, float* mu, const float* sigma, float* weight, float* exp_avg, float* exp_avg_sq,
+                     int* status, int num_em_loop, float alpha, double lr, double beta1, double beta2, double adam_eps,
+                     double tau, float lamda, int C, int K, int D, int cap, cudaStream_t st) {
+    CUtensorMap mh, ml;
+    const uint64_t rows = (uint64_t)C * cap;
+    if (!make_map_f16(&mh, shadow_h, rows, D, TR) || !make_map_f16(&ml, shadow_l, rows, D, TR)) return MGP_ERR_UNSUPPORTED;
+    EmTcParams prm;
+    prm.xx = shadow_xx; prm.order = order; prm.sched = sched; prm.mu = mu; prm.sigma = sigma; prm.weight = weight;
+    prm.exp_avg = exp_avg; prm.exp_avg_sq = exp_avg_sq; prm.status = status;
+    prm.adam = make_adam(lr, beta1, beta2, adam_eps);
+    prm.alpha = alpha; prm.tau = (float)tau; prm.omtau = (float)(1.0 - tau); prm.lamda = lamda;
+    prm.num_em_loop = num_em_loop; prm.C = C; prm.K = K; prm.cap = cap;
+#define MGP_EMTC(DD, KK)                                                                                            \
+    do {                                                                                                            \
+        const size_t smem = em_tc_smem<DD>(KK);                                                                     \
+        MGP_CUDA(cudaFuncSetAttribute(em_tc_kernel<DD, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        em_tc_kernel<DD, KK><<<C, 256, smem, st>>>(mh, ml, prm);                                                    \
+    } while (0)
+    if (D == 128) {
+        if (K <= 5) MGP_EMTC(128, 5);
+        else if (K <= 10) MGP_EMTC(128, 10);
+        else MGP_EMTC(128, 16);
+    } else {
+        if (K <= 5) MGP_EMTC(256, 5);
+        else if (K <= 10) MGP_EMTC(256, 10);
+        else MGP_EMTC(256, 16);
+    }
+#undef MGP_EMTC
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}

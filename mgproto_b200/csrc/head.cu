@@ -296,7 +296,7 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
         }
         for (int k = warp; k < K; k += 8) {
             float ls = 0.f;
-            for (int d = lane; d < D; d += 32) ls += logf(sgg[k * D + d]);
+            for (int d = lane; d < D; d += 32) ls += logf(sgg[k * D + d]) + 0.5f * MGP_LOG_2PI;   // per-dim terms
             ls = warp_sum(ls);
             if (lane == 0) s_ls[k] = ls;
         }
@@ -373,7 +373,7 @@ head_top1_kernel(const unsigned long long* __restrict__ best, const float* __res
                 }
 #pragma unroll
                 for (int i = 0; i < 5; ++i)
-                    if (k0 + i < ke) lp[(k0 + i) * HWp + n] = -0.5f * (float)D * MGP_LOG_2PI - s_ls[k0 + i] - 0.5f * q[i];
+                    if (k0 + i < ke) lp[(k0 + i) * HWp + n] = -s_ls[k0 + i] - 0.5f * q[i];
             }
         }
         __syncthreads();

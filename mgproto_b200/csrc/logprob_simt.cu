@@ -27,10 +27,10 @@ __global__ void proto_prep_kernel(const float* __restrict__ sigma, float eps, fl
     for (int d = lane; d < D; d += 32) {
         float s = sigma[(size_t)p * D + d];
         rinv[(size_t)p * D + d] = 1.0f / (s + eps);
-        ls += logf(s + eps_log);
+        ls += logf(s + eps_log) + 0.5f * MGP_LOG_2PI;   // per-dim terms: no 470 - 470 cancellation at D = 512
     }
     ls = warp_sum(ls);
-    if (lane == 0) cst[p] = -0.5f * (float)D * MGP_LOG_2PI - ls;
+    if (lane == 0) cst[p] = -ls;
 }
 
 // PROTO_ON_I: rows i of the tile are prototypes and columns j are patches (BPHW layouts);

@@ -12,7 +12,7 @@
 // pass is not).  Power-of-two scalings keep the lo parts in fp16's normal range and are undone
 // exactly in the epilogue.
 //
-// Structure (one persistent CTA per SM, 8 warps):
+// Structure (one persistent CTA per SM, 12 warps):
 //   warp 0   TMA producer: prototype (A) K-blocks through an S-stage mbarrier ring
 //   warp 3   TMA producer of the x tile (B, 128 patches x Kg), resident per n-tile, double-buffered when
 //            sigma is isotropic so the next n-tile is prefetched under the current one's MMAs
@@ -28,11 +28,10 @@
 #include <cuda_fp16.h>
 
 #include "mgp_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
-constexpr int NT_MAX = 256;      // patches per tile (UMMA N): 256 (192 with the TMA-store epilogue) when sigma is
-                                 // isotropic, else 128
 constexpr int LAYOUT_NP_TMA = 3; // internal: [N,P] output written by TMA bulk tensor stores from a shared-memory stage
 constexpr int LAYOUT_BPHW_TMA = 4;   // internal: [B,P,HW] log p through a 3-D tensor map (boxes clipped at image ends)
 constexpr int LAYOUT_NEGP_TMA = 5;   // internal: [B,P,HW] -exp(log p), same
@@ -43,101 +42,11 @@ constexpr int KB = 64;           // K elements per smem block (128 B rows, SWIZZ
 constexpr int SUB_BYTES = 128 * KB * 2;   // one [128 x 64] fp16 block = 16 KiB
 constexpr float X_SCALE = 256.0f;
 
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// ------------------------------------------------------------------------------------------ PTX (tc_ptx.cuh)
+using namespace mgp_tc;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (uint32_t it = 0; !ok; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!ok && (it & 1023u) == 1023u) {              // a protocol bug must fault, not hang the device
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-// 1-D bulk async copy global -> shared (TMA engine, no tensor map): operands are stored in global memory
-// already tiled and 128B-swizzled exactly as the UMMA descriptors read them, so a whole 16/32 KiB block
-// is one contiguous transfer.
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// byte offset of element (row r < 128, col k < 64) inside a [128 x 64] fp16 block, K-major SWIZZLE_128B:
-// 8-row groups of 1024 B, 16-byte chunks XOR-ed with the row index
-__host__ __device__ __forceinline__ uint32_t swz_off(int r, int k) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-// start>>4 | LBO(16 B)=1 <<16 | SBO(1024 B)=64 <<32 | version 1 <<46 | layout SWIZZLE_128B(2) <<61
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int n_tile) {
-    return (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(PT >> 4) << 24);
-}
+// kind::f16 instruction descriptor of the [PT prototypes x n_tile patches] tile, both operands K-major
+__device__ __forceinline__ uint32_t make_idesc(int n_tile) { return umma_idesc_f16(PT, n_tile); }
 
 // ------------------------------------------------------------------------------------------ prep
 // Prototype side: Bh/Bl [P, 2D] fp16 = split of scale_p * [ w | -2 w mu ]; e0,e1,e2 [P]; noniso flag.
@@ -159,7 +68,7 @@ __global__ void tc_proto_prep_kernel(const float* __restrict__ mu, const float* 
         const float r = 1.0f / (s + eps);
         const float w = r * r;
         const float m = mr[d];
-        ls += logf(s + eps_log);
+        ls += logf(s + eps_log) + 0.5f * MGP_LOG_2PI;   // per-dim terms (they cancel for sigma = 1/sqrt(2 pi))
         c2 = fmaf(w * m, m, c2);
         mx = fmaxf(mx, fmaxf(w, fabsf(2.0f * w * m)));
     }
@@ -182,7 +91,7 @@ __global__ void tc_proto_prep_kernel(const float* __restrict__ mu, const float* 
     }
     if (lane == 0) {
         const float r0 = 1.0f / (s0 + eps);
-        e0[p] = -0.5f * (float)D * MGP_LOG_2PI - ls - 0.5f * c2;
+        e0[p] = -ls - 0.5f * c2;
         e1[p] = -0.5f / (scale * X_SCALE);
         e2[p] = -0.5f * r0 * r0;                          // used only when every prototype is isotropic
         if (!same) atomicOr(noniso, 1);
@@ -622,35 +531,9 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
-
-// [rows, cols] fp16 row-major, box = 64 cols x 128 rows, 128 B swizzle; OOB rows read as zero
+// [rows, cols] fp16 row-major, box = 64 cols x box_rows, 128 B swizzle; OOB rows read as zero (tc_ptx.cuh)
 bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * sizeof(__half)};
-    cuuint32_t box[2] = {KB, box_rows};
-    cuuint32_t es[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return make_map_f16(m, ptr, rows, cols, box_rows);
 }
 
 // output [N, P] fp32 row-major, box = 32 prototypes x 32 patches, no swizzle (TMA-store epilogue)

@@ -38,6 +38,48 @@ class MemoryBank(nn.Module):
         self.register_buffer("head", torch.zeros(num_classes, dtype=torch.int32), persistent=False)
         self.register_buffer("updated", torch.zeros(num_classes, dtype=torch.uint8), persistent=False)
         self.register_buffer("mem_len", torch.zeros(num_classes, dtype=torch.int64))
+        # tensor-core operand copy of the bank (fp16 hi / lo of 256 * row, |row|^2), built on first use by update_GMM
+        # and kept in step by the enqueue scatter; plain attributes (not buffers): derived data, never checkpointed
+        self._shadow = None
+        self._shadow_key = None
+        # a bank enqueue still running on a side stream (multi-GPU overlap): (event, keep-alive tensors)
+        self._pending = None
+
+    # -- cross-stream safety: every reader / writer of the bank tensors on another stream waits for a pending enqueue
+    def set_pending(self, event, keepalive=None):
+        self._pending = (event, keepalive)
+
+    def wait_pending(self):
+        pend = self.__dict__.get("_pending")
+        if pend is not None:
+            self._pending = None             # (cleared first: fetching self.bank below re-enters __getattr__)
+            torch.cuda.current_stream(self._buffers["bank"].device).wait_event(pend[0])
+
+    # -- shadow ---------------------------------------------------------------------------------------------
+    def _bank_key(self):
+        b = self._buffers["bank"]
+        return (b.data_ptr(), b._version, str(b.device))
+
+    def shadow_if_valid(self):
+        """(shadow_h, shadow_l, shadow_xx) if the shadow exists and the fp32 bank has not been written by anything but
+        the enqueue kernel since it was built, else None."""
+        if self._shadow is not None and self._shadow_key == self._bank_key():
+            return self._shadow
+        return None
+
+    def ensure_shadow(self):
+        """Build (or rebuild after an external write to ``bank``: torch bumps its version counter) the shadow."""
+        sh = self.shadow_if_valid()
+        if sh is None:
+            b = self._buffers["bank"]
+            if self._shadow is None or self._shadow[0].device != b.device:
+                self._shadow = (torch.empty(b.shape, dtype=torch.float16, device=b.device),
+                                torch.empty(b.shape, dtype=torch.float16, device=b.device),
+                                torch.empty(b.shape[:2], dtype=torch.float32, device=b.device))
+            ops.bank_shadow_sync(b, *self._shadow)
+            self._shadow_key = self._bank_key()
+            sh = self._shadow
+        return sh
 
     # -- reference-compatible views ---------------------------------------------------------
     def linear(self) -> torch.Tensor:
@@ -51,6 +93,8 @@ class MemoryBank(nn.Module):
         return lin * mask[:, :, None]
 
     def __getattr__(self, name):
+        if name in ("bank", "mem_len", "head", "updated") and self.__dict__.get("_pending") is not None:
+            self.wait_pending()              # a side-stream enqueue may still be writing these (model.py head())
         m = _CLS_RE.match(name)
         if m is not None and "_buffers" in self.__dict__ and "bank" in self._buffers:
             return self.linear()[int(m.group(1))]

@@ -114,8 +114,7 @@ class MGProto(nn.Module):
         self.em_shard = False            # True: shard bank rows over the ranks + all-reduce the EM statistics per loop
         self.overlap_enqueue = True      # multi-GPU: all-gather + enqueue on a side stream, behind the backward
         self._side_stream = None
-        self._enqueue_done = None
-        self._keepalive = None
+        self._em_status = None           # int32[1] on the device: set by the tensor-core EM kernel if sigma was not isotropic
         self._adam_step_dev = None       # int32[1] on the device: Adam step count, advanced by update_GMM's planner
         self._adam_step_seen = None      # host value the device counter was seeded from / last folded back to
         self._em_dirty = False           # device counter ahead of prototype_optimizer.state[...]['step']
@@ -160,17 +159,18 @@ class MGProto(nn.Module):
                     side.wait_stream(cur)
                     with torch.cuda.stream(side):
                         t1, r1, g1 = all_gather_mined(top1, rows, gt, self.em_group)
-                        ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, r1, t1, g1)
+                        ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, r1, t1, g1, shadow=q.shadow_if_valid())
                         done = torch.cuda.Event()
                         done.record(side)
                         del t1, r1, g1                                            # side-stream blocks: reused in stream order
-                    self._enqueue_done = done
-                    self._keepalive = (top1, rows, gt)
+                    # the bank remembers the event: every later access to its tensors (mem_len in the training loop,
+                    # state_dict, push, update_GMM) first makes its stream wait for this enqueue
+                    q.set_pending(done, (top1, rows, gt))
                 else:
                     if self.em_group is not None:                                 # batch-sharded replicas
                         from .parallel import all_gather_mined
                         top1, rows, gt = all_gather_mined(top1, rows, gt, self.em_group)
-                    ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, rows, top1, gt)
+                    ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, rows, top1, gt, shadow=q.shadow_if_valid())
                 self.iteration_counter += 1                                       # ref :252
         return logits
 
@@ -239,15 +239,15 @@ class MGProto(nn.Module):
     def wait_enqueue(self):
         """Make the current stream wait for a bank enqueue still running on the side stream (multi-GPU path).
         update_GMM and the next enqueue call it; call it before reading ``queue`` tensors on another stream."""
-        if self._enqueue_done is not None:
-            torch.cuda.current_stream().wait_event(self._enqueue_done)
-            self._enqueue_done = None
-            self._keepalive = None
+        self.queue.wait_pending()
 
     def sync_optimizer_state(self):
         """Fold the Adam step count kept on the device (advanced by every update_GMM without touching the host)
         into ``prototype_optimizer.state[...]['step']``.  Synchronises; call it before inspecting or saving the
         optimiser.  update_GMM itself never waits for the device."""
+        if self._em_status is not None and int(self._em_status.item()) != 0:
+            raise RuntimeError("mgproto_b200: update_GMM's tensor-core kernel found anisotropic sigma after the host check "
+                               "said isotropic (prototype_covs was modified in place without a version bump?)")
         if self._em_dirty:
             v = int(self._adam_step_dev.item())
             st = self.prototype_optimizer.state[self.prototype_means]
@@ -309,8 +309,16 @@ class MGProto(nn.Module):
             self._em_dirty = False
         lr, (b1, b2), eps = group["lr"], group["betas"], group["eps"]
         if world == 1:
+            # tensor-core path (csrc/em_tc.cu): K <= 16, D in {128, 256}, sigma constant over d inside every prototype
+            # (one cached host check: prototype_covs never changes in the reference's loop) -- needs the bank's shadow
+            shadow, iso = None, False
+            if 2 <= K <= 16 and D in (128, 256) and ops.sigma_is_isotropic(self.prototype_covs):
+                shadow, iso = q.ensure_shadow(), True
+                if self._em_status is None or self._em_status.device != dev:
+                    self._em_status = torch.zeros(1, dtype=torch.int32, device=dev)
             ops.update_gmm(q.bank, q.updated, q.mem_len, mu, sg, wt, st["exp_avg"], st["exp_avg_sq"], self._adam_step_dev,
-                           order, sched, stats, n_split, L, self.alpha, lr, b1, b2, eps, self.tau)
+                           order, sched, stats, n_split, L, self.alpha, lr, b1, b2, eps, self.tau, shadow=shadow,
+                           sigma_iso=iso, status=self._em_status)
             self._em_dirty = True
             return
         ops.em_plan(q.updated, q.mem_len, order, sched, 0, cap, L, adam_step=self._adam_step_dev)

@@ -15,7 +15,7 @@ from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, M
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP, check)
 
 __all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_level0", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
-           "bank_linearize", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
+           "bank_linearize", "bank_shadow_sync", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
 MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE,
@@ -301,8 +301,9 @@ def mined_gather(xhat_nd, idx, gt, HW, C, K):
     return top1, rows
 
 
-def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt):
-    """ref model.py:228-250 + utils/memory.py:31-73, in place on (bank, mem_len, head, updated)."""
+def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt, shadow=None):
+    """ref model.py:228-250 + utils/memory.py:31-73, in place on (bank, mem_len, head, updated); ``shadow`` =
+    (shadow_h, shadow_l, shadow_xx) keeps the tensor-core operand copy of the bank in step (MemoryBank.ensure_shadow)."""
     bank = _req(bank, torch.float32, "bank")
     C, cap, D = bank.shape
     B, K = top1.shape
@@ -315,10 +316,23 @@ def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt):
     if rows.shape != (B, K, D) or gt.shape != (B,):
         raise RuntimeError("mgproto_b200: enqueue shape mismatch")
     plan = torch.empty((B * K,), device=bank.device, dtype=torch.int32)
+    sh = shadow if shadow is not None else (None, None, None)
     check(_lib.load().mgp_bank_enqueue(bank.data_ptr(), mem_len.data_ptr(), head.data_ptr(), updated.data_ptr(),
-                                       rows.data_ptr(), top1.data_ptr(), gt.data_ptr(), plan.data_ptr(), B, C, K, D,
-                                       cap, _stream()), "mgp_bank_enqueue")
+                                       rows.data_ptr(), top1.data_ptr(), gt.data_ptr(), plan.data_ptr(), _p(sh[0]),
+                                       _p(sh[1]), _p(sh[2]), B, C, K, D, cap, _stream()), "mgp_bank_enqueue")
     _count(2)
+
+
+def bank_shadow_sync(bank, shadow_h, shadow_l, shadow_xx):
+    """(Re)build the fp16 hi/lo + |row|^2 shadow of the whole bank (include/mgproto_b200.h: mgp_bank_shadow_sync)."""
+    bank = _req(bank, torch.float32, "bank")
+    C, cap, D = bank.shape
+    _req(shadow_h, torch.float16, "shadow_h")
+    _req(shadow_l, torch.float16, "shadow_l")
+    _req(shadow_xx, torch.float32, "shadow_xx")
+    check(_lib.load().mgp_bank_shadow_sync(bank.data_ptr(), shadow_h.data_ptr(), shadow_l.data_ptr(), shadow_xx.data_ptr(),
+                                           C, cap, D, _stream()), "mgp_bank_shadow_sync")
+    _count(1)
 
 
 def bank_linearize(bank, mem_len, head):
@@ -368,16 +382,22 @@ def em_update(stats, n_split, n_rows_total, order, sched, mu_ckd, sigma_ckd, wei
 
 
 def update_gmm(bank, updated, mem_len, mu_ckd, sigma_ckd, weight_cp, exp_avg, exp_avg_sq, adam_step, order, sched, stats,
-               n_split, num_em_loop, alpha, lr, beta1, beta2, adam_eps, tau, lamda=1.0):
-    """ref model.py:277-301, single replica: plan + zero-gradient replays + num_em_loop x (stats, step) in one call."""
+               n_split, num_em_loop, alpha, lr, beta1, beta2, adam_eps, tau, lamda=1.0, shadow=None, sigma_iso=False,
+               status=None):
+    """ref model.py:277-301, single replica: plan + zero-gradient replays + num_em_loop x (stats, step) in one call.
+    With ``shadow`` (MemoryBank.ensure_shadow()), ``sigma_iso`` and a device int32 ``status`` word the supported
+    shapes run on the tensor cores (csrc/em_tc.cu)."""
     C, cap, D = bank.shape
     K = mu_ckd.shape[1]
-    check(_lib.load().mgp_update_gmm(bank.data_ptr(), updated.data_ptr(), mem_len.data_ptr(), mu_ckd.data_ptr(),
+    sh = shadow if shadow is not None else (None, None, None)
+    tc = shadow is not None and sigma_iso and status is not None
+    check(_lib.load().mgp_update_gmm(bank.data_ptr(), _p(sh[0]), _p(sh[1]), _p(sh[2]), 1 if sigma_iso else 0, _p(status),
+                                     updated.data_ptr(), mem_len.data_ptr(), mu_ckd.data_ptr(),
                                      sigma_ckd.data_ptr(), weight_cp.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                      adam_step.data_ptr(), order.data_ptr(), sched.data_ptr(), stats.data_ptr(),
                                      int(n_split), int(num_em_loop), float(alpha), float(lr), float(beta1), float(beta2),
                                      float(adam_eps), float(tau), float(lamda), C, K, D, cap, _stream()), "mgp_update_gmm")
-    _count(int(_lib.load().mgp_update_gmm_launches(K, D, cap, int(num_em_loop))))
+    _count(int(_lib.load().mgp_update_gmm_launches(K, D, cap, int(num_em_loop), 1 if tc else 0)))
 
 
 def em_estep(x_nd, mu_kd, sigma_kd, pi_k, want_log_resp=True, want_score=True):

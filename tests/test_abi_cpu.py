@@ -27,10 +27,37 @@ def test_header_symbols_exported():
     assert sorted(_lib.SIGNATURES) == names, set(_lib.SIGNATURES) ^ set(names)
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype in include/mgproto_b200.h, argument by argument (pointer / int / float / double / size_t),
+    against the ctypes table: a float bound where the header says double would silently corrupt the call."""
+    import ctypes as C
+    from mgproto_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "mgproto_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|const char\s*\*)\s+(mgp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def kind(arg):
+        arg = arg.strip()
+        if "*" in arg:
+            return "ptr"
+        for k in ("double", "float", "size_t", "int"):
+            if re.search(r"\b%s\b" % k, arg):
+                return k
+        raise AssertionError(arg)
+
+    cmap = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int: "int", C.c_float: "float", C.c_double: "double",
+            C.c_size_t: "size_t"}
+    for name, args in protos:
+        want = [] if args.strip() in ("", "void") else [kind(a) for a in args.split(",")]
+        got = [cmap[t] for t in _lib.SIGNATURES[name][1]]
+        assert got == want, (name, got, want)
+
+
 def test_abi_version_and_errors():
     from mgproto_b200 import _lib
     lib = _lib.load()
-    assert lib.mgp_abi_version() == 1
+    assert lib.mgp_abi_version() == 2
     assert b"invalid" in lib.mgp_error_string(-1)
     assert b"supported" in lib.mgp_error_string(-2)
     # argument validation happens before any CUDA call, so it is testable without a GPU

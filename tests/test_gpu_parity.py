@@ -55,7 +55,7 @@ def _separated(v):
 def test_library_loaded_and_abi():
     from mgproto_b200 import _lib
     lib = _lib.load()
-    assert lib.mgp_abi_version() == 1
+    assert lib.mgp_abi_version() == 2
 
 
 def test_normalize(golden):

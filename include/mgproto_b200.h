@@ -64,6 +64,9 @@ int mgp_has_tensor_core_path(void);
  * cluster launch where the shape allows, 0 = always the multi-launch path (identical arithmetic, used by the
  * parity tests to cross-check the two).  Returns the previous value, or MGP_ERR_INVALID for an unknown key. */
 int mgp_set_option(const char* key, int value);
+/* Profiling hooks.  key "em_tc_prof": p = device buffer of 64*8 int64 (or NULL to stop) that the tensor-core EM kernel
+ * fills with clock64 stamps of its pipeline phases for class `arg` (tools/em_tc_prof.py prints them). */
+int mgp_debug_set_ptr(const char* key, void* p, int arg);
 
 /* ---- a1  l2_normalize + rearrange -------------------------------------------------------
  * ref: model.py:40-41, :210-211, :431-432.
@@ -136,6 +139,12 @@ int mgp_head_bwd(const float* grad_logits, const float* logits, const float* val
                  const float* xhat_nd, const float* inv_norm, const float* mu,
                  const float* sigma, void* ws, size_t ws_bytes, float* g_x_nchw, int B, int HW,
                  int C, int K, int D, int T, void* stream);
+
+/* ref: model.py:188-206 (global_max_pooling_gmm_topT) as a stand-alone call on PROBABILITIES sims [B,P,HW]:
+ * vals [B,P,T] = the T largest over HW, descending; idx [B,P,T] their patch indices; feats [B,P,D,T] (optional, NULL
+ * to skip; 4*B*P*D*T bytes) = x_nchw[b, :, idx[b,p,t]] -- the reference's max_feat, [B,C,K,D,T] once viewed. */
+int mgp_topt_pool(const float* sims_bphw, const float* x_nchw, float* vals, int32_t* idx, float* feats,
+                  int B, int HW, int C, int K, int D, int T, void* stream);
 
 /* ---- a8/a9  enqueue into the per-class FIFO bank -----------------------------------------
  * ref: model.py:225-250, utils/memory.py:31-73.
@@ -243,6 +252,12 @@ int mgp_em_estep(const float* x, const float* mu, const float* sigma, const floa
  * pi_out [K], mu_out [K,D], sigma_out [K,D]. */
 int mgp_em_mstep_closed(const float* x, const float* log_resp, float alpha, float* pi_out,
                         float* mu_out, float* sigma_out, int n, int K, int D, void* stream);
+/* ref: model.py:367-401 (_m_step_diversified) on explicit rows: pi_out [K] = (sum_n r + 1e-10) / n and
+ * grad_out [K,D] = d gmm_loss / d mu (weighted log-likelihood term + lamda * diversity term), r the smoothed
+ * responsibilities of log_resp; ws_nk [n*K] fp32 scratch.  The caller feeds grad_out to the optimiser step. */
+int mgp_em_mstep_div(const float* x, const float* log_resp, const float* mu, const float* sigma,
+                     float alpha, float lamda, float* ws_nk, float* pi_out, float* grad_out, int n,
+                     int K, int D, void* stream);
 
 /* ---- a17  training loss on the head output (optional fused helper) ------------------------------
  * ref: train_and_test.py:37-41, :55.  out [B,C,T] log evidences, gt [B] ->

@@ -22,6 +22,7 @@ SIGNATURES = {
     "mgp_error_string": (C.c_char_p, [_i]),
     "mgp_has_tensor_core_path": (_i, []),
     "mgp_set_option": (_i, [C.c_char_p, _i]),
+    "mgp_debug_set_ptr": (_i, [C.c_char_p, _vp, _i]),
     "mgp_normalize_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_normalize_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_logprob_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
@@ -44,6 +45,8 @@ SIGNATURES = {
                            _d, _d, _d, _d, _d, _f, _vp, _i, _i, _i, _i, _vp]),
     "mgp_em_estep": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_mstep_closed": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mgp_em_mstep_div": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mgp_topt_pool": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "mgp_mine_ce": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mgp_push_argmin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }

@@ -53,10 +53,21 @@ class VGGFeatures(nn.Module):
 
 def _make(kind, ctor):
     def factory(pretrained=False, **kw):
+        """``pretrained=True`` (what the reference's main.py passes): load ``$MGPROTO_PRETRAINED_DIR/<arch>.pth`` (a
+        torchvision state dict) if it exists; otherwise warn and keep the random initialisation -- there is no network
+        on the target boxes, and raising here would make ``construct_MGProto(..., pretrained=True)`` unusable."""
+        net = ctor(weights=None, **kw)
         if pretrained:
-            raise RuntimeError("pretrained weights need a local file; load them with load_state_dict "
-                               "(no network in this environment)")
-        return kind(ctor(weights=None, **kw))
+            import os
+            import warnings
+            import torch
+            path = os.path.join(os.environ.get("MGPROTO_PRETRAINED_DIR", ""), ctor.__name__ + ".pth")
+            if os.environ.get("MGPROTO_PRETRAINED_DIR") and os.path.exists(path):
+                net.load_state_dict(torch.load(path, map_location="cpu"))
+            else:
+                warnings.warn("mgproto_b200: pretrained=True but no local weights (%s; set MGPROTO_PRETRAINED_DIR): "
+                              "backbone keeps its random initialisation" % (path or ctor.__name__ + ".pth"))
+        return kind(net)
     return factory
 
 
@@ -71,6 +82,46 @@ base_architecture_to_features = {
     "vgg16": _make(VGGFeatures, tvm.vgg16), "vgg16_bn": _make(VGGFeatures, tvm.vgg16_bn),
     "vgg19": _make(VGGFeatures, tvm.vgg19), "vgg19_bn": _make(VGGFeatures, tvm.vgg19_bn),
 }
+
+
+def conv_info(features: nn.Module):
+    """(kernel sizes, strides, paddings) of the backbone's main path, the input of the receptive-field walk (ref
+    models/*_features.py ``conv_info``): every Conv2d / pooling layer in order, residual ``downsample`` branches
+    excluded.  For ResNet / DenseNet the reference's metadata also counts the stem max-pool (3, 2, 1) although its
+    forward skips it (models/resnet_features.py:140-142, densenet_features.py:119-121); that quirk is kept so the
+    numbers equal the reference's."""
+    ks, st, pd = [], [], []
+
+    def one(v):
+        return int(v[0] if isinstance(v, (tuple, list)) else v)
+    stem_pool_pending = isinstance(features, (ResNetFeatures, DenseNetFeatures))
+    for name, m in features.named_modules():
+        if "downsample" in name:
+            continue
+        if isinstance(m, (nn.Conv2d, nn.MaxPool2d, nn.AvgPool2d)):
+            ks.append(one(m.kernel_size)); st.append(one(m.stride)); pd.append(one(m.padding))
+            if stem_pool_pending and isinstance(m, nn.Conv2d):
+                ks.append(3); st.append(2); pd.append(1)
+                stem_pool_pending = False
+    return ks, st, pd
+
+
+def proto_layer_rf_info(img_size, kernel_sizes, strides, paddings, prototype_kernel_size=1):
+    """[n, jump, receptive-field size, centre of the first field] of the prototype layer (ref
+    utils/receptive_field.py:111-141): the standard recurrence n' = floor((n + 2p - k)/s) + 1, j' = j s,
+    r' = r + (k - 1) j, start' = start + ((k - 1)/2 - p) j, followed by the prototype kernel as a VALID, stride-1 layer."""
+    import math
+    n, j, r, start = img_size, 1, 1, 0.5
+    for k, s, p in zip(kernel_sizes, strides, paddings):
+        n = math.floor((n + 2 * p - k) / s) + 1
+        r = r + (k - 1) * j
+        start = start + ((k - 1) / 2 - p) * j
+        j = j * s
+    k = prototype_kernel_size
+    n = math.ceil(float(n - k + 1))
+    r = r + (k - 1) * j
+    start = start + ((k - 1) / 2) * j
+    return [n, j, r, start]
 
 
 def out_channels(features: nn.Module) -> int:

@@ -31,6 +31,14 @@ int mgp_opt_em_fused() {
     if (g_mgp_em_fused < 0) g_mgp_em_fused = getenv("MGP_EM_UNFUSED") ? 0 : 1;
     return g_mgp_em_fused;
 }
+void mgp_em_tc_set_prof(void* p, int cls);   // em_tc.cu
+extern "C" int mgp_debug_set_ptr(const char* key, void* p, int arg) {
+    if (!key) return MGP_ERR_INVALID;
+#ifdef MGP_WITH_TC
+    if (strcmp(key, "em_tc_prof") == 0) { mgp_em_tc_set_prof(p, arg); return MGP_OK; }
+#endif
+    return MGP_ERR_INVALID;
+}
 int g_mgp_em_tc = -1;
 int mgp_opt_em_tc() {
     if (g_mgp_em_tc < 0) g_mgp_em_tc = getenv("MGP_EM_NO_TC") ? 0 : 1;

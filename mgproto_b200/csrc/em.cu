@@ -33,7 +33,7 @@ int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* sh
                      double tau, float lamda, int C, int K, int D, int cap, cudaStream_t st);
 
 namespace {
-
+using namespace mgp_em;
 
 __global__ void __launch_bounds__(1024)
 em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_len, int32_t* __restrict__ order,

@@ -48,10 +48,17 @@ struct EmTcParams {
     float* exp_avg;
     float* exp_avg_sq;
     int* status;                  // set to 1 if a class turned out to have anisotropic sigma (its update is skipped)
+    long long* prof;              // profiling (mgp_debug_set_ptr("em_tc_prof")): clock64 stamps of class `prof_class`
     AdamCfg adam;
     float alpha, tau, omtau, lamda;
-    int num_em_loop, C, K, cap;
+    int num_em_loop, C, K, cap, prof_class;
 };
+// stamp layout: prof[(tile_ctr * 8 + phase)]; phases: 0 TMA issued, 1 TMA landed, 2 E-step MMAs issued, 3 E-step done
+// (seen by thread 0), 4 epilogue done, 5 statistics MMAs issued, 6 loop tail entered, 7 loop tail done
+#define MGP_PROF(ctr, ph)                                                                          \
+    do {                                                                                           \
+        if (prm.prof && c == prm.prof_class && (ctr) < 64) prm.prof[(ctr) * 8 + (ph)] = clock64();  \
+    } while (0)
 
 // byte offset of element (row r < 16, col k) of a [16 x D] fp16 operand stored K-major SWIZZLE_128B as D/64 blocks of
 // [16 rows x 128 B]: 16-byte chunks XOR-ed with (row & 7)
@@ -276,6 +283,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
             const uint32_t par = tile_ctr & 1u;
             if (tid == ISSUER) {
                 if (tile_ctr > 0) mbar_wait(bar_s, (tile_ctr - 1) & 1u);     // previous statistics MMAs have read X and R
+                MGP_PROF(tile_ctr, 0);
                 mbar_expect_tx(bar_tma, 2 * X_BYTES);
                 const int row0 = c * cap + t * TR;
 #pragma unroll
@@ -284,6 +292,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                     tma_load_2d(base + o_xl + ch * CH_BYTES, &map_l, ch * 64, row0, bar_tma);
                 }
                 mbar_wait(bar_tma, par);
+                MGP_PROF(tile_ctr, 1);
                 tc_fence_after();
                 // E-step: D_e[row, k] = sum_d X[row, d] A[k, d]   (3 passes: hi.hi + lo.hi + hi.lo)
 #pragma unroll
@@ -297,6 +306,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                     tc_mma_f16(d_e, xh, al, idesc_e, 1u);
                 }
                 tc_commit(bar_e);
+                MGP_PROF(tile_ctr, 2);
             }
             if (warp < 4) {
                 // ---- E-step epilogue: thread = bank row
@@ -304,6 +314,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                 const bool valid = row < cap;
                 const float xxv = valid ? __ldg(prm.xx + (size_t)c * cap + row) : 0.f;
                 mbar_wait(bar_e, par);
+                if (tid == 0) MGP_PROF(tile_ctr, 3);
                 tc_fence_after();
                 uint32_t q[16];
                 tmem_ld16(d_e + ((uint32_t)(warp * 32) << 16), q);
@@ -337,6 +348,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                     }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tc_fence_before();
+                if (tid == 0) MGP_PROF(tile_ctr, 4);
             }
             __syncthreads();
             if (tid == ISSUER) {
@@ -357,8 +369,10 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                     }
                 }
                 tc_commit(bar_s);
+                MGP_PROF(tile_ctr, 5);
             }
         }
+        if (tid == 0) MGP_PROF(tile_ctr - 1, 6);
         // ---- S0 over the class, S1 from TMEM
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
@@ -402,6 +416,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         }
         __syncthreads();                                              // every reader of s_mu / s_s0 is done
         if (tid < K) s_pi[tid] = prm.tau * s_pi[tid] + prm.omtau * ((s_s0[tid] + EM_EPS) / n_rows);   // ref :385, :399, :297
+        if (tid == 0) MGP_PROF(tile_ctr - 1, 7);
     }
     replay(step0 + L * (ord + 1), L * (n_active - ord - 1));
     write_back();
@@ -422,6 +437,10 @@ size_t em_tc_smem(int kt) {
 
 }  // namespace
 
+static long long* g_em_tc_prof = nullptr;
+static int g_em_tc_prof_class = 0;
+void mgp_em_tc_set_prof(void* p, int cls) { g_em_tc_prof = reinterpret_cast<long long*>(p); g_em_tc_prof_class = cls; }
+
 bool mgp_em_tc_supported(int K, int D, int cap) {
     return K >= 2 && K <= 16 && (D == 128 || D == 256) && cap >= 1 && get_encode() != nullptr;
 }
@@ -439,6 +458,7 @@ int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* sh
     prm.adam = make_adam(lr, beta1, beta2, adam_eps);
     prm.alpha = alpha; prm.tau = (float)tau; prm.omtau = (float)(1.0 - tau); prm.lamda = lamda;
     prm.num_em_loop = num_em_loop; prm.C = C; prm.K = K; prm.cap = cap;
+    prm.prof = g_em_tc_prof; prm.prof_class = g_em_tc_prof_class;
 #define MGP_EMTC(DD, KK)                                                                                            \
     do {                                                                                                            \
         const size_t smem = em_tc_smem<DD>(KK);                                                                     \

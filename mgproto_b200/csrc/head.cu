@@ -149,7 +149,9 @@ template <int R, int NR, bool FROM_NP>
 __global__ void __launch_bounds__(256, (R <= 8) ? 3 : 1)
 head_select_kernel(const float* __restrict__ logp, const float* __restrict__ weight, const int64_t* __restrict__ gt,
                    float* __restrict__ logits, float* __restrict__ vals, int32_t* __restrict__ idx, int HW, int C,
-                   int K, int T, int CT) {
+                   int K, int T, int CT, int is_prob) {
+    // is_prob: the input rows already hold p = exp(log p) (mgp_topt_pool: the reference's
+    // global_max_pooling_gmm_topT takes probabilities); the order is the same, the values are passed through
     extern __shared__ float win[];  // [CT*K][T] exp(log p) of the winners  (+ [HW][CT*K+1] tile when FROM_NP)
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * CT;
@@ -194,7 +196,7 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
                 const bool own = gl0 >= 0 && pl >= gl0 && pl < gl0 + K;     // done with all levels below
                 if (pl < npl && !own && lane < T) {
                     const int p = c0 * K + pl;
-                    const float e = expf(v[i]);  // ref model.py:215; levels >= 1 alias level 0 (ref :218-221)
+                    const float e = is_prob ? v[i] : expf(v[i]);  // ref model.py:215; levels >= 1 alias level 0 (ref :218-221)
                     if (lane == 0) win[pl * T] = e;
                     vals[((size_t)b * P + p) * T + lane] = e;
                     idx[((size_t)b * P + p) * T + lane] = ix[i];
@@ -219,7 +221,7 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
             const int pl = pl0 + i;
             if (pl < fe && lane < T) {
                 const int p = c0 * K + pl;
-                const float e = expf(v[i]);  // ref model.py:215
+                const float e = is_prob ? v[i] : expf(v[i]);  // ref model.py:215
                 win[pl * T + lane] = e;
                 vals[((size_t)b * P + p) * T + lane] = e;
                 idx[((size_t)b * P + p) * T + lane] = ix[i];
@@ -227,6 +229,7 @@ head_select_kernel(const float* __restrict__ logp, const float* __restrict__ wei
         }
     }
     __syncthreads();
+    if (weight == nullptr) return;                                             // pooling only (mgp_topt_pool)
     for (int e = threadIdx.x; e < nc * T; e += blockDim.x) {
         const int cl = e / T, t = e - cl * T;
         const int c = c0 + cl;
@@ -806,8 +809,9 @@ __global__ void push_argmin_kernel(const float* __restrict__ logp, const int64_t
 }  // namespace
 
 static int head_select_launch(const float* logp, int from_np, const float* weight_cp, const int64_t* gt, float* logits,
-                              float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream) {
-    if (!logp || !weight_cp || !logits || !vals || !idx) return MGP_ERR_INVALID;
+                              float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream,
+                              int is_prob = 0) {
+    if (!logp || !vals || !idx || (!is_prob && (!weight_cp || !logits))) return MGP_ERR_INVALID;
     if (B <= 0 || HW <= 0 || C <= 0 || K <= 0 || T <= 0) return MGP_ERR_INVALID;
     if (T > 32 || T > HW || HW > 1024) return MGP_ERR_UNSUPPORTED;
     int CT = 64 / K;
@@ -826,7 +830,7 @@ static int head_select_launch(const float* logp, int from_np, const float* weigh
         MGP_CUDA(cudaFuncSetAttribute(head_select_kernel<RR, NRR, NP>,                                               \
                                       cudaFuncAttributePreferredSharedMemoryCarveout, NP ? 100 : 25));               \
         head_select_kernel<RR, NRR, NP><<<grid, 256, smem, st>>>(logp, weight_cp, gt, logits, vals, idx, HW, C, K,   \
-                                                                 T, CT);                                             \
+                                                                 T, CT, is_prob);                                    \
     } while (0)
 #define MGP_LAUNCH_SEL(RR, NRR)                                                                                      \
     do {                                                                                                             \
@@ -853,6 +857,34 @@ extern "C" int mgp_head_select(const float* logp_bphw, const float* weight_cp, c
 extern "C" int mgp_head_select_np(const float* logp_np, const float* weight_cp, const int64_t* gt, float* logits,
                                   float* vals, int32_t* idx, int B, int HW, int C, int K, int T, void* stream) {
     return head_select_launch(logp_np, 1, weight_cp, gt, logits, vals, idx, B, HW, C, K, T, stream);
+}
+
+// feats[b, p, d, t] = x[b, d, idx[b, p, t]]  (ref model.py:197-206: the T gathers of global_max_pooling_gmm_topT)
+namespace {
+__global__ void topt_gather_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, float* __restrict__ feats,
+                                   int HW, int P, int D, int T) {
+    const int b = blockIdx.y, p = blockIdx.x;
+    __shared__ int s_i[32];
+    if (threadIdx.x < T) s_i[threadIdx.x] = idx[((size_t)b * P + p) * T + threadIdx.x];
+    __syncthreads();
+    float* dst = feats + ((size_t)b * P + p) * D * T;
+    const float* src = x + (size_t)b * D * HW;
+    for (int e = threadIdx.x; e < D * T; e += blockDim.x) {
+        const int d = e / T, t = e - d * T;
+        dst[e] = src[(size_t)d * HW + s_i[t]];
+    }
+}
+}  // namespace
+
+extern "C" int mgp_topt_pool(const float* sims_bphw, const float* x_nchw, float* vals, int32_t* idx, float* feats, int B,
+                             int HW, int C, int K, int D, int T, void* stream) {
+    if (!sims_bphw || !vals || !idx || (feats && !x_nchw) || D <= 0) return MGP_ERR_INVALID;
+    int rc = head_select_launch(sims_bphw, 0, nullptr, nullptr, nullptr, vals, idx, B, HW, C, K, T, stream, 1);
+    if (rc != MGP_OK || !feats) return rc;
+    dim3 grid(C * K, B);
+    topt_gather_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, idx, feats, HW, C * K, D, T);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
 }
 
 extern "C" int mgp_head_select_top1(const uint64_t* best, const float* xhat_nd, const float* mu, const float* sigma,

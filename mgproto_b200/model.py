@@ -2,7 +2,11 @@
 
 Same constructor, methods, attributes and state-dict keys as the reference's ``model.MGProto``
 (``/root/reference/model.py:77-482``), so the reference's ``train_and_test.py`` / ``push.py`` /
-``main.py`` loops drive it unchanged.  The backbone, add-on convs, embedding and losses are
+``main.py`` loops drive it unchanged.  Differences a caller can observe (also listed in INTEGRATION.md):
+``memory_updated_cls`` is a read-only snapshot of device flags; ``proto_layer_rf_info`` is computed for the
+torchvision backbones by ``backbones.proto_layer_rf_info`` (the reference's receptive-field walk) and is ``None`` for
+custom ``features``; ``construct_MGProto(pretrained=True)`` loads weights from ``$MGPROTO_PRETRAINED_DIR`` if set and
+otherwise warns and keeps the random initialisation (no network on the target boxes).  The backbone, add-on convs, embedding and losses are
 ordinary PyTorch; everything between the add-on output ``[B,D,H,W]`` and the log mixture
 evidences ``[B,C,T]`` -- plus the memory bank and its EM update -- runs in the hand-written
 sm_100a kernels of ``libmgproto_b200.so``.  There is no CPU path: tensors must be on a CUDA
@@ -122,7 +126,9 @@ class MGProto(nn.Module):
     # -- reference attribute: CPU bool flags ----------------------------------------------------
     @property
     def memory_updated_cls(self):
-        self.wait_enqueue()
+        """The reference's CPU bool tensor (model.py:167), here a read-only snapshot of the device flags
+        ``queue.updated`` (this read synchronises; the training path never needs it -- write through
+        ``queue.updated``)."""
         return self.queue.updated.bool().cpu()
 
     # -- backbone side (stock PyTorch) ----------------------------------------------------------
@@ -258,6 +264,14 @@ class MGProto(nn.Module):
             self._adam_step_seen = v
             self._em_dirty = False
 
+    def _hook_optimizer(self):
+        """optimizer.state_dict() (checkpointing in the reference's loop) must see the Adam step count update_GMM keeps
+        on the device: fold it in right before the state is read."""
+        opt = self.prototype_optimizer
+        if getattr(opt, "_mgp_hooked", None) is not self and hasattr(opt, "register_state_dict_pre_hook"):
+            opt.register_state_dict_pre_hook(lambda _o: self.sync_optimizer_state())
+            opt._mgp_hooked = self
+
     def _adam_state(self):
         opt, p = self.prototype_optimizer, self.prototype_means
         st = opt.state[p]
@@ -298,10 +312,12 @@ class MGProto(nn.Module):
             return self._update_GMM_generic(order, sched, stats, n_split, r0, r1, world)
 
         st = self._adam_state()
+        self._hook_optimizer()
         host_step = int(st["step"])
-        if self._adam_step_dev is None or self._adam_step_dev.device != dev or host_step != self._adam_step_seen:
+        if self._adam_step_dev is None or self._adam_step_dev.device != dev or self._adam_step_seen is None or \
+                host_step != self._adam_step_seen:
             # first call, or the optimiser state was replaced / stepped elsewhere: (re)seed the device counter
-            if self._em_dirty and self._adam_step_dev is not None:
+            if self._em_dirty and self._adam_step_dev is not None and self._adam_step_seen is not None:
                 host_step += int(self._adam_step_dev.item()) - self._adam_step_seen   # keep the steps not folded back yet
                 st["step"] = torch.tensor(float(host_step)) if torch.is_tensor(st["step"]) else host_step
             self._adam_step_dev = torch.tensor([host_step], dtype=torch.int32, device=dev)
@@ -390,6 +406,55 @@ class MGProto(nn.Module):
         pi, mu, var = ops.em_mstep_closed(x2, log_resp.reshape(x2.shape[0], -1), self.alpha)
         return pi.view(1, -1, 1), mu.unsqueeze(0), var.unsqueeze(0)
 
+    def _class_of_view(self, mu_old):
+        """The class whose slice of ``prototype_means`` ``mu_old`` views (the reference's autograd finds it through
+        the indexing op ``self.prototype_means[_c]``, model.py:295)."""
+        p = self.prototype_means
+        C, K, D = p.shape
+        off = mu_old.data_ptr() - p.data_ptr()
+        step = K * D * p.element_size()
+        if mu_old.numel() != K * D or off < 0 or off % step != 0 or off // step >= C or \
+                mu_old.untyped_storage().data_ptr() != p.untyped_storage().data_ptr():
+            raise RuntimeError("_m_step_diversified: mu_old must be a view prototype_means[c] of the parameter the "
+                               "prototype optimiser owns (ref model.py:295): the gradient goes to that class")
+        return off // step
+
+    def _m_step_diversified(self, x, log_resp, mu_old, var_old, pi_old, eps=1e-10, lamda=1.0):
+        """ref model.py:367-401: one diversified M-step = gradient of the GMM loss w.r.t. the class's means (fused
+        kernel, equal to the reference's autograd gradient: SURVEY KA6) + ``prototype_optimizer.step()`` on the whole
+        mean tensor (zero gradient outside the class, as the reference's backward leaves it).
+        -> (pi [1,K,1], mu_old, var_old); sigma untouched, exactly like the reference."""
+        if abs(eps - 1e-10) > 1e-16:
+            raise RuntimeError("_m_step_diversified: the kernels are built for the reference's eps = 1e-10")
+        if self.prototype_optimizer is None:
+            raise RuntimeError("_m_step_diversified needs model.prototype_optimizer (ref main.py:223-228)")
+        x2 = self._check_size(x).squeeze(1)
+        n, D = x2.shape
+        c = self._class_of_view(mu_old)
+        K = self.num_prototypes_per_class
+        with torch.no_grad():
+            pi, grad = ops.em_mstep_div(x2.detach(), log_resp.detach().reshape(n, K), mu_old.detach().reshape(K, D),
+                                        var_old.detach().reshape(K, D), self.alpha, lamda)
+            self.sync_optimizer_state()                      # fold update_GMM's device-side step count in first
+            self.prototype_optimizer.zero_grad()
+            full = torch.zeros_like(self.prototype_means)
+            full[c].copy_(grad)
+            self.prototype_means.grad = full
+            self.prototype_optimizer.step()
+            self._adam_step_seen = None                      # the optimiser stepped outside update_GMM: reseed next time
+        return pi.view(1, K, 1), mu_old, var_old
+
+    def global_max_pooling_gmm_topT(self, similarities, conv_features, mine_T=20):
+        """ref model.py:188-206: ``similarities`` [B,C,K,H,W] (probabilities), ``conv_features`` [B,D,H,W] ->
+        (values [B,P,T] sorted descending, features [B,C,K,D,T], indices [B,C,K,T] int64).  forward() does not call
+        this (the fused head mines inside the kernels and never builds the 5 GB feature gather); it exists for code
+        written against the reference's method."""
+        B, C, K, H, W = similarities.shape
+        vals, idx, feats = ops.topt_pool(similarities.detach().reshape(B, C * K, H * W), conv_features.detach(),
+                                         int(mine_T), C, K)
+        D = conv_features.shape[1]
+        return vals, feats.view(B, C, K, D, int(mine_T)), idx.view(B, C, K, int(mine_T)).long()
+
     def _score(self, x, mu, var, pi, as_average=True, eps=1e-10):
         """ref model.py:403-421."""
         x2 = self._check_size(x).squeeze(1)
@@ -434,9 +499,12 @@ class MGProto(nn.Module):
 def construct_MGProto(base_architecture, pretrained=True, img_size=224, prototype_shape=(2000, 128, 1, 1),
                       num_classes=200, prototype_activation_function="log", add_on_layers_type="bottleneck",
                       sz_embedding=32, mem_capacity=1000, mine_K=10):
-    """ref model.py:485-510 (receptive-field metadata is not computed: the hot path never reads it)."""
+    """ref model.py:485-510."""
+    from .backbones import conv_info, proto_layer_rf_info
     features = base_architecture_to_features[base_architecture](pretrained=pretrained)
-    return MGProto(features=features, img_size=img_size, prototype_shape=prototype_shape, proto_layer_rf_info=None,
+    ks, st, pd = conv_info(features)
+    rf = proto_layer_rf_info(img_size, ks, st, pd, prototype_shape[2])
+    return MGProto(features=features, img_size=img_size, prototype_shape=prototype_shape, proto_layer_rf_info=rf,
                    num_classes=num_classes, init_weights=True,
                    prototype_activation_function=prototype_activation_function,
                    add_on_layers_type=add_on_layers_type, sz_embedding=sz_embedding, mem_capacity=mem_capacity,

@@ -15,7 +15,7 @@ from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, M
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP, check)
 
 __all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_level0", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
-           "bank_linearize", "bank_shadow_sync", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "push_argmin", "mine_cross_entropy",
+           "bank_linearize", "bank_shadow_sync", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "em_mstep_div", "topt_pool", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
 MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE,
@@ -47,8 +47,51 @@ def _count(n: int):
     _launches += n
 
 
+_op_device = None      # device of the op being issued: every tensor argument of one op must live on it
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current stream OF THE OP'S DEVICE (not of whatever device happens to be current)."""
+    return torch.cuda.current_stream(_op_device).cuda_stream
+
+
+class _on_device:
+    """Wraps an op: all tensor arguments must share one CUDA device, and the op runs with that device current (the C
+    library launches on the current context; a model on cuda:1 called from a thread whose current device is cuda:0
+    must not dereference foreign pointers)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.__name__ = getattr(fn, "__name__", "op")
+        self.__doc__ = fn.__doc__
+
+    def __call__(self, *args, **kw):
+        global _op_device
+        dev = None
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, (tuple, list)):
+                cand = [t for t in a if isinstance(t, torch.Tensor)]
+            else:
+                cand = [a] if isinstance(a, torch.Tensor) else []
+            for t in cand:
+                if t.is_cuda:
+                    if dev is None:
+                        dev = t.device
+                    elif t.device != dev:
+                        raise RuntimeError("mgproto_b200: %s got tensors on %s and %s" % (self.__name__, dev, t.device))
+        prev = _op_device
+        if dev is None or dev.index == torch.cuda.current_device():
+            _op_device = dev
+            try:
+                return self.fn(*args, **kw)
+            finally:
+                _op_device = prev
+        with torch.cuda.device(dev):
+            _op_device = dev
+            try:
+                return self.fn(*args, **kw)
+            finally:
+                _op_device = prev
 
 
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
@@ -70,6 +113,7 @@ def _math(math) -> int:
 
 
 # ----------------------------------------------------------------------------------- a1
+@_on_device
 def normalize_fwd(x_bdhw: torch.Tensor, want_nchw: bool = False):
     """ref model.py:210-211.  -> (xhat [N,D], inv_norm [N], xhat_nchw [B,D,H,W] | None)."""
     x = _req(x_bdhw, torch.float32, "x")
@@ -86,6 +130,7 @@ def normalize_fwd(x_bdhw: torch.Tensor, want_nchw: bool = False):
 
 
 # ----------------------------------------------------------------------------------- a2/a3/a16
+@_on_device
 def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, eps=0.0, eps_log=0.0,
             math="auto", ws=None, out=None, return_ws=False):
     """ref model.py:256-275 / :323-336.  xhat [N,D], mu/sigma [P,D] ->
@@ -125,6 +170,7 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
     return (out, ws) if return_ws else out
 
 
+@_on_device
 def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto", ws=None, return_ws=False):
     """Per (image, prototype) max / arg-max of log p over the patches, computed in the tensor-core kernel's
     epilogue without writing log p (MGP_OUT_TOP1_BP).  -> packed int64 [B,P] (see include/mgproto_b200.h), or None
@@ -157,6 +203,7 @@ def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto", ws=None, return_w
     return (best, ws) if return_ws else best
 
 
+@_on_device
 def head_select_top1(best, xhat_nd, mu_pd, sigma_pd, weight_cp, gt, T, C, K, HW):
     """Labelled head from the packed level-0 results (ref model.py:188-206, :218-222, :254): full top-T only for
     every image's own class (exact fp32 log p of its K prototypes).  -> (logits [B,C,T], vals, idx [B,P,T]);
@@ -176,6 +223,7 @@ def head_select_top1(best, xhat_nd, mu_pd, sigma_pd, weight_cp, gt, T, C, K, HW)
 
 
 # ----------------------------------------------------------------------------------- a4-a7
+@_on_device
 def head_select(logp, weight_cp, gt, T, C, K, B=None, HW=None):
     """ref model.py:188-206, :218-222, :254 -> (logits [B,C,T], vals [B,P,T], idx [B,P,T] int32).
     logp is [B,P,HW], or [N,P] (then pass B and HW)."""
@@ -247,17 +295,24 @@ class HeadFunction(torch.autograd.Function):
             return (None,) * 7
         logits, vals, idx, wt, gt, xhat, inv, mu, sg = ctx.saved_tensors
         B, HW, C, K, D, T, H, W = ctx.dims
-        g = _req(g_logits.contiguous(), torch.float32, "grad_logits")
-        lib = _lib.load()
-        nbytes = lib.mgp_head_bwd_ws_bytes(B, HW, C * K, D)
-        ws = torch.empty((nbytes,), device=g.device, dtype=torch.uint8)
-        gx = torch.empty((B, D, H, W), device=g.device, dtype=torch.float32)
-        check(lib.mgp_head_bwd(g.data_ptr(), logits.data_ptr(), vals.data_ptr(), idx.data_ptr(), wt.data_ptr(),
-                               gt.data_ptr() if ctx.has_gt else 0, xhat.data_ptr(), inv.data_ptr(), mu.data_ptr(),
-                               sg.data_ptr(), ws.data_ptr(), nbytes, gx.data_ptr(), B, HW, C, K, D, T, _stream()),
-              "mgp_head_bwd")
-        _count(3)
+        gx = head_backward(g_logits, logits, vals, idx, wt, gt if ctx.has_gt else None, xhat, inv, mu, sg, ctx.dims)
         return gx, None, None, None, None, None, None
+
+
+@_on_device
+def head_backward(g_logits, logits, vals, idx, wt, gt, xhat, inv, mu, sg, dims):
+    """d logits / d features through the selected patches only (mgp_head_bwd): -> grad of the add-on features [B,D,H,W]."""
+    B, HW, C, K, D, T, H, W = dims
+    g = _req(g_logits.contiguous(), torch.float32, "grad_logits")
+    lib = _lib.load()
+    nbytes = lib.mgp_head_bwd_ws_bytes(B, HW, C * K, D)
+    ws = torch.empty((nbytes,), device=g.device, dtype=torch.uint8)
+    gx = torch.empty((B, D, H, W), device=g.device, dtype=torch.float32)
+    check(lib.mgp_head_bwd(g.data_ptr(), logits.data_ptr(), vals.data_ptr(), idx.data_ptr(), wt.data_ptr(), _p(gt),
+                           xhat.data_ptr(), inv.data_ptr(), mu.data_ptr(), sg.data_ptr(), ws.data_ptr(), nbytes,
+                           gx.data_ptr(), B, HW, C, K, D, T, _stream()), "mgp_head_bwd")
+    _count(3)
+    return gx
 
 
 def head_level0(x_add, mu_ckd, sigma_ckd, weight_cp, math="auto"):
@@ -286,6 +341,7 @@ def head_forward(x_add, mu_ckd, sigma_ckd, weight_cp, gt, T, math="auto"):
 
 
 # ----------------------------------------------------------------------------------- a8/a9
+@_on_device
 def mined_gather(xhat_nd, idx, gt, HW, C, K):
     """ref model.py:225-226: (top1 [B,K] int32, rows [B,K,D]) of every image's GT-class prototypes."""
     _req(xhat_nd, torch.float32, "xhat")
@@ -301,6 +357,7 @@ def mined_gather(xhat_nd, idx, gt, HW, C, K):
     return top1, rows
 
 
+@_on_device
 def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt, shadow=None):
     """ref model.py:228-250 + utils/memory.py:31-73, in place on (bank, mem_len, head, updated); ``shadow`` =
     (shadow_h, shadow_l, shadow_xx) keeps the tensor-core operand copy of the bank in step (MemoryBank.ensure_shadow)."""
@@ -323,6 +380,7 @@ def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt, shadow=None):
     _count(2)
 
 
+@_on_device
 def bank_shadow_sync(bank, shadow_h, shadow_l, shadow_xx):
     """(Re)build the fp16 hi/lo + |row|^2 shadow of the whole bank (include/mgproto_b200.h: mgp_bank_shadow_sync)."""
     bank = _req(bank, torch.float32, "bank")
@@ -335,6 +393,7 @@ def bank_shadow_sync(bank, shadow_h, shadow_l, shadow_xx):
     _count(1)
 
 
+@_on_device
 def bank_linearize(bank, mem_len, head):
     bank = _req(bank, torch.float32, "bank")
     C, cap, D = bank.shape
@@ -350,6 +409,7 @@ def em_stat_stride(K, D, with_s2=False) -> int:
     return int(_lib.load().mgp_em_stat_stride(K, D, 1 if with_s2 else 0))
 
 
+@_on_device
 def em_plan(updated, mem_len, order, sched, step0, cap, num_em_loop, adam_step=None):
     C = updated.numel()
     check(_lib.load().mgp_em_plan(updated.data_ptr(), mem_len.data_ptr(), order.data_ptr(), sched.data_ptr(),
@@ -357,6 +417,7 @@ def em_plan(updated, mem_len, order, sched, step0, cap, num_em_loop, adam_step=N
     _count(1)
 
 
+@_on_device
 def em_stats(bank, order, mu_ckd, sigma_ckd, weight_cp, alpha, stats, n_split, row_begin=0, row_end=None,
              with_s2=False):
     C, cap, D = bank.shape
@@ -369,6 +430,7 @@ def em_stats(bank, order, mu_ckd, sigma_ckd, weight_cp, alpha, stats, n_split, r
     _count(1)
 
 
+@_on_device
 def em_update(stats, n_split, n_rows_total, order, sched, mu_ckd, sigma_ckd, weight_cp, exp_avg, exp_avg_sq, em_loop,
               num_em_loop, phase, lr, beta1, beta2, adam_eps, tau, lamda=1.0, grad_out=None, only_class=-1,
               with_s2=False):
@@ -381,6 +443,7 @@ def em_update(stats, n_split, n_rows_total, order, sched, mu_ckd, sigma_ckd, wei
     _count(1)
 
 
+@_on_device
 def update_gmm(bank, updated, mem_len, mu_ckd, sigma_ckd, weight_cp, exp_avg, exp_avg_sq, adam_step, order, sched, stats,
                n_split, num_em_loop, alpha, lr, beta1, beta2, adam_eps, tau, lamda=1.0, shadow=None, sigma_iso=False,
                status=None):
@@ -400,6 +463,7 @@ def update_gmm(bank, updated, mem_len, mu_ckd, sigma_ckd, weight_cp, exp_avg, ex
     _count(int(_lib.load().mgp_update_gmm_launches(K, D, cap, int(num_em_loop), 1 if tc else 0)))
 
 
+@_on_device
 def em_estep(x_nd, mu_kd, sigma_kd, pi_k, want_log_resp=True, want_score=True):
     """ref model.py:303-321 / :403-421 -> (log_resp [n,K] | None, score [n] | None)."""
     x = _req(x_nd.contiguous(), torch.float32, "x")
@@ -416,6 +480,7 @@ def em_estep(x_nd, mu_kd, sigma_kd, pi_k, want_log_resp=True, want_score=True):
     return lr, sc
 
 
+@_on_device
 def em_mstep_closed(x_nd, log_resp_nk, alpha):
     """ref model.py:338-365 -> (pi [K], mu [K,D], sigma [K,D])."""
     x = _req(x_nd.contiguous(), torch.float32, "x")
@@ -431,21 +496,71 @@ def em_mstep_closed(x_nd, log_resp_nk, alpha):
     return pi, mu, sg
 
 
+@_on_device
+def em_mstep_div(x_nd, log_resp_nk, mu_kd, sigma_kd, alpha, lamda=1.0):
+    """ref model.py:367-401 on explicit rows -> (pi_new [K], grad [K,D] = d gmm_loss / d mu)."""
+    x = _req(x_nd.contiguous(), torch.float32, "x")
+    lr = _req(log_resp_nk.contiguous(), torch.float32, "log_resp")
+    mu = _req(mu_kd.contiguous(), torch.float32, "mu")
+    sg = _req(sigma_kd.contiguous(), torch.float32, "sigma")
+    n, D = x.shape
+    K = mu.shape[0]
+    if lr.shape != (n, K) or mu.shape != (K, D) or sg.shape != (K, D):
+        raise RuntimeError("mgproto_b200: shape mismatch in em_mstep_div")
+    ws = torch.empty((n, K), device=x.device, dtype=torch.float32)
+    pi = torch.empty((K,), device=x.device, dtype=torch.float32)
+    grad = torch.empty((K, D), device=x.device, dtype=torch.float32)
+    check(_lib.load().mgp_em_mstep_div(x.data_ptr(), lr.data_ptr(), mu.data_ptr(), sg.data_ptr(), float(alpha),
+                                       float(lamda), ws.data_ptr(), pi.data_ptr(), grad.data_ptr(), n, K, D, _stream()),
+          "mgp_em_mstep_div")
+    _count(2)
+    return pi, grad
+
+
+@_on_device
+def topt_pool(sims_bphw, x_nchw, T, C, K, want_feats=True):
+    """ref model.py:188-206 on probabilities [B,P,HW] -> (vals [B,P,T], idx [B,P,T] int32, feats [B,P,D,T] | None)."""
+    sm = _req(sims_bphw.contiguous(), torch.float32, "similarities")
+    B, P, HW = sm.shape
+    if P != C * K:
+        raise RuntimeError("mgproto_b200: shape mismatch in topt_pool")
+    vals = torch.empty((B, P, T), device=sm.device, dtype=torch.float32)
+    idx = torch.empty((B, P, T), device=sm.device, dtype=torch.int32)
+    feats, xp, D = None, 0, 1
+    if want_feats:
+        x = _req(x_nchw.contiguous(), torch.float32, "conv_features")
+        D = x.shape[1]
+        if x.shape[0] != B or x.numel() != B * D * HW:
+            raise RuntimeError("mgproto_b200: conv_features must be [B,D,H,W] with H*W == HW")
+        feats = torch.empty((B, P, D, T), device=sm.device, dtype=torch.float32)
+        xp = x.data_ptr()
+    check(_lib.load().mgp_topt_pool(sm.data_ptr(), xp, vals.data_ptr(), idx.data_ptr(), _p(feats), B, HW, C, K, D, int(T),
+                                    _stream()), "mgp_topt_pool")
+    _count(2 if want_feats else 1)
+    return vals, idx, feats
+
+
 # ----------------------------------------------------------------------------------- a17 (optional)
+@_on_device
+def _mine_ce(out, gt, mine_coef):
+    o = _req(out.contiguous(), torch.float32, "output")
+    g = _req(gt.contiguous(), torch.int64, "target")
+    B, C, T = o.shape
+    loss_b = torch.empty((B,), device=o.device, dtype=torch.float32)
+    grad = torch.empty_like(o)
+    check(_lib.load().mgp_mine_ce(o.data_ptr(), g.data_ptr(), loss_b.data_ptr(), grad.data_ptr(), B, C, T,
+                                  float(mine_coef), _stream()), "mgp_mine_ce")
+    _count(1)
+    return loss_b, grad
+
+
 class MineCEFunction(torch.autograd.Function):
     """loss = CE(out[:,:,0], gt) + mine_coef * mean_{t>=1} CE(out[:,:,t], gt) (ref train_and_test.py:37-41,:55)
     with value and gradient from one kernel."""
 
     @staticmethod
     def forward(ctx, out, gt, mine_coef):
-        o = _req(out.contiguous(), torch.float32, "output")
-        g = _req(gt.contiguous(), torch.int64, "target")
-        B, C, T = o.shape
-        loss_b = torch.empty((B,), device=o.device, dtype=torch.float32)
-        grad = torch.empty_like(o)
-        check(_lib.load().mgp_mine_ce(o.data_ptr(), g.data_ptr(), loss_b.data_ptr(), grad.data_ptr(), B, C, T,
-                                      float(mine_coef), _stream()), "mgp_mine_ce")
-        _count(1)
+        loss_b, grad = _mine_ce(out, gt, mine_coef)
         ctx.save_for_backward(grad)
         return loss_b.sum()
 
@@ -460,6 +575,7 @@ def mine_cross_entropy(out, gt, mine_coef=0.2):
 
 
 # ----------------------------------------------------------------------------------- f1
+@_on_device
 def push_argmin(logp_bphw, labels, C, K):
     """ref push.py:125-158 -> (arg [B,K] int32 flat HW index, val [B,K] = -p at the argmin)."""
     lp = _req(logp_bphw, torch.float32, "logp")

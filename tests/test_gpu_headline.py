@@ -184,15 +184,35 @@ def test_headline_head_vs_fp64_oracle_batch16():
 
 
 # ------------------------------------------------------------------------------------------------ EM
-def _run_em(g, math, fused, dtype_note=""):
+EM_PATHS = {"tc": (1, 1), "fused": (0, 1), "multilaunch": (0, 0)}      # (em_tc, em_fused) switches of mgp_set_option
+
+
+class em_path:
+    """Select which update_GMM implementation the library takes: tensor-core kernel (csrc/em_tc.cu), fp32 cluster
+    kernel, or the multi-launch path (identical semantics; the tests cross-check all three)."""
+
+    def __init__(self, name):
+        self.want = EM_PATHS[name]
+
+    def __enter__(self):
+        from mgproto_b200 import _lib
+        lib = _lib.load()
+        self.prev = (lib.mgp_set_option(b"em_tc", self.want[0]), lib.mgp_set_option(b"em_fused", self.want[1]))
+
+    def __exit__(self, *a):
+        from mgproto_b200 import _lib
+        lib = _lib.load()
+        lib.mgp_set_option(b"em_tc", self.prev[0])
+        lib.mgp_set_option(b"em_fused", self.prev[1])
+
+
+def _run_em(g, math, path):
     C, K, D, T, cap = (int(g[k]) for k in "C K D T cap".split())
-    from mgproto_b200 import _lib
     net = _net(C, K, D, T, cap, g["mu"], g["sg"], g["wt"], math, lr=float(g["lr"]))
     am, av, flags, short, step0 = HC.em_state(C, K, D)
     _fill_bank(net, HC.bank_rows(C, K, D, cap, g["mu"]), short, int(g["short_len"]))
     _seed_adam(net, am, av, step0)
-    prev = _lib.load().mgp_set_option(b"em_fused", 1 if fused else 0)
-    try:
+    with em_path(path):
         with torch.no_grad():
             net.head(_t(g["x"]), _t(g["gt"], torch.int64))                    # the labelled step's enqueue
         outs = []
@@ -205,21 +225,19 @@ def _run_em(g, math, fused, dtype_note=""):
             outs.append((net.prototype_means.detach().cpu().numpy().copy(),
                          np.stack([w[i, i * K:(i + 1) * K] for i in range(C)])))
         net.sync_optimizer_state()
-    finally:
-        _lib.load().mgp_set_option(b"em_fused", prev)
     return net, outs
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused", "multilaunch"])
+@pytest.mark.parametrize("path", ["tc", "fused", "multilaunch"])
 @pytest.mark.parametrize("math", ["auto", "fp32"])
-def test_headline_update_gmm_vs_reference(hl, math, fused):
+def test_headline_update_gmm_vs_reference(hl, math, path):
     """Two update_GMM calls (156 + 137 active classes, 5 flagged-but-short classes, Adam at step 1000) after the
     labelled step's enqueue: mu, pi, Adam moments and step vs the unmodified reference."""
     g = hl
-    net, outs = _run_em(g, math, fused)
+    net, outs = _run_em(g, math, path)
     (mu0, pi0), (mu1, pi1) = outs
     e0, e1 = normwise(mu0[::3], g["mu_after0"]), normwise(mu1, g["mu_after1"])
-    print("mu norm-wise error vs reference (%s, %s): %.2e / %.2e" % (math, "fused" if fused else "multi", e0, e1))
+    print("mu norm-wise error vs reference (%s, %s): %.2e / %.2e" % (math, path, e0, e1))
     assert e0 < TOL and e1 < TOL
     # per class (a class that barely moved must still be right): error relative to that class's largest |mu|
     d = np.abs(mu1.astype(np.float64) - g["mu_after1"]).reshape(mu1.shape[0], -1).max(1)
@@ -268,11 +286,6 @@ def test_variant_shapes_head_and_em_vs_fp64_oracle(C, K, D, sigma_mode):
     # EM: all classes flagged, Adam pre-seeded
     rows = HC.bank_rows(C, K, D, cap, mu, seed=22)
     am, av, flags, short, step0 = HC.em_state(C, K, D, seed=23, n_active=(C,), n_short=2, step0=(5000 if D == 256 else 500))
-    _fill_bank(net, rows, short, cap - 11)
-    _seed_adam(net, am, av, step0)
-    net.queue.updated |= _t(flags[0], torch.uint8)
-    net.update_GMM()
-    net.sync_optimizer_state()
     bank = O.MemoryBankOracle(C, D, cap, dtype=np.float64)
     bank.data[:] = rows
     bank.mem_len[:] = cap
@@ -281,11 +294,20 @@ def test_variant_shapes_head_and_em_vs_fp64_oracle(C, K, D, sigma_mode):
     adam = O.AdamOracle((C, K, D), lr=3e-3)
     adam.m, adam.v, adam.t = f64(am), f64(av), step0
     mu_ref, wt_ref, _ = O.update_gmm(bank, flags[0], f64(mu), f64(sg), f64(wt), adam)
-    assert normwise(net.prototype_means.detach().cpu().numpy(), mu_ref) < TOL
-    mv = normwise(net.prototype_means.detach().cpu().numpy().astype(np.float64) - mu, mu_ref - mu)
-    assert mv < 2e-3, mv
-    np.testing.assert_allclose(net.last_layer.weight.cpu().numpy(), wt_ref, rtol=TOL, atol=1e-9)
-    st = net.prototype_optimizer.state[net.prototype_means]
-    assert int(st["step"]) == adam.t
-    assert normwise(st["exp_avg"].cpu().numpy(), adam.m) < TOL
-    assert normwise(st["exp_avg_sq"].cpu().numpy(), adam.v) < TOL
+    for path in ("tc", "multilaunch"):           # (tc falls through to the fp32 kernels where it does not apply)
+        net = _net(C, K, D, T, cap, mu, sg, wt, "auto")
+        _fill_bank(net, rows, short, cap - 11)
+        _seed_adam(net, am, av, step0)
+        net.queue.updated |= _t(flags[0], torch.uint8)
+        with em_path(path):
+            net.update_GMM()
+            net.sync_optimizer_state()
+        got = net.prototype_means.detach().cpu().numpy()
+        e_mu, e_mv = normwise(got, mu_ref), normwise(got.astype(np.float64) - mu, mu_ref - mu)
+        print("variant C%d K%d D%d %s [%s]: mu %.2e movement %.2e" % (C, K, D, sigma_mode, path, e_mu, e_mv))
+        assert e_mu < TOL and e_mv < 1e-3, (path, e_mu, e_mv)
+        np.testing.assert_allclose(net.last_layer.weight.cpu().numpy(), wt_ref, rtol=TOL, atol=1e-9)
+        st = net.prototype_optimizer.state[net.prototype_means]
+        assert int(st["step"]) == adam.t
+        assert normwise(st["exp_avg"].cpu().numpy(), adam.m) < TOL
+        assert normwise(st["exp_avg_sq"].cpu().numpy(), adam.v) < TOL

@@ -27,7 +27,7 @@ int mgp_opt_em_fused();   // abi.cu
 int mgp_opt_em_tc();      // abi.cu
 // em_tc.cu
 bool mgp_em_tc_supported(int K, int D, int cap);
-int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* shadow_xx, const int32_t* order,
+int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* shadow_xx, const float* bias_corr, const int32_t* order,
                      const int32_t* sched, float* mu, const float* sigma, float* weight, float* exp_avg, float* exp_avg_sq,
                      int* status, int num_em_loop, float alpha, double lr, double beta1, double beta2, double adam_eps,
                      double tau, float lamda, int C, int K, int D, int cap, cudaStream_t st);
@@ -37,7 +37,9 @@ using namespace mgp_em;
 
 __global__ void __launch_bounds__(1024)
 em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_len, int32_t* __restrict__ order,
-               int32_t* __restrict__ sched, int32_t* __restrict__ adam_step, int step0, int C, int cap, int num_em_loop) {
+               int32_t* __restrict__ sched, int32_t* __restrict__ adam_step, int step0, int C, int cap, int num_em_loop,
+               AdamCfg adam, float* __restrict__ bias_corr) {
+    __shared__ int s_plan[2];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const bool act = updated[c] != 0 && mem_len[c] >= (int64_t)cap;   // ref model.py:283, :289
         order[c] = act ? 1 : 0;
@@ -54,9 +56,29 @@ em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_le
         const int s0 = adam_step ? adam_step[0] : step0;
         sched[1] = s0;
         if (adam_step) adam_step[0] = s0 + r * num_em_loop;
+        s_plan[0] = r; s_plan[1] = s0;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) updated[c] = 0;      // ref model.py:287, :301
+    if (bias_corr) {
+        // Step-dependent factors of this call's Adam steps s0+1 .. s0+n (n = r*L), evaluated ONCE here in double (torch:
+        // Python doubles, narrowed last) instead of per class in the EM kernel:
+        //   [2i] = lr / (1 - b1^t), [2i+1] = sqrt(1 - b2^t), t = s0+1+i;  then b1^i, b2^(i/2), b2^i for i = 0..n
+        const int n = s_plan[0] * num_em_loop, s0 = s_plan[1];
+        float* t_b1 = bias_corr + 2 * n;
+        float* t_b2h = t_b1 + (n + 1);
+        float* t_b2 = t_b2h + (n + 1);
+        for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+            if (i < n) {
+                const double t = (double)(s0 + i + 1);
+                bias_corr[2 * i] = (float)(adam.lr / (1.0 - pow(adam.beta1, t)));
+                bias_corr[2 * i + 1] = (float)sqrt(1.0 - pow(adam.beta2, t));
+            }
+            t_b1[i] = (float)pow(adam.beta1, (double)i);
+            t_b2h[i] = (float)pow(adam.beta2, 0.5 * (double)i);
+            t_b2[i] = (float)pow(adam.beta2, (double)i);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1295,7 +1317,7 @@ extern "C" int mgp_em_plan(uint8_t* updated, const int64_t* mem_len, int32_t* or
                            int32_t* adam_step, int step0, int C, int cap, int num_em_loop, void* stream) {
     if (!updated || !mem_len || !order || !sched || C <= 0 || cap <= 0 || num_em_loop <= 0) return MGP_ERR_INVALID;
     em_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(updated, mem_len, order, sched, adam_step, step0, C, cap,
-                                                         num_em_loop);
+                                                         num_em_loop, make_adam(1.0, 0.9, 0.999, 1e-8), nullptr);
     MGP_CHECK_LAUNCH();
     return MGP_OK;
 }
@@ -1441,14 +1463,20 @@ extern "C" int mgp_update_gmm(const float* bank, const void* shadow_h, const voi
         return MGP_ERR_INVALID;
     int rc = em_validate(C, K, D, cap, num_em_loop);                 // before the planner clears flags / counts steps
     if (rc != MGP_OK) return rc;
-    rc = mgp_em_plan(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop, stream);
-    if (rc != MGP_OK) return rc;
 #ifdef MGP_WITH_TC
-    if (shadow_h && shadow_l && shadow_xx && status && em_tc_applies(K, D, cap, sigma_iso))
-        return mgp_em_tc_launch(shadow_h, shadow_l, shadow_xx, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq,
+    if (shadow_h && shadow_l && shadow_xx && status && em_tc_applies(K, D, cap, sigma_iso) &&
+        (size_t)5 * num_em_loop * C + 3 <= (size_t)C * n_split * mgp_em_stat_stride(K, D, 0)) {
+        // tensor-core path: the planner also tabulates the steps' Adam bias corrections into the (otherwise unused) stats scratch
+        em_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop,
+                                                             make_adam(lr, beta1, beta2, adam_eps), stats);
+        MGP_CHECK_LAUNCH();
+        return mgp_em_tc_launch(shadow_h, shadow_l, shadow_xx, stats, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq,
                                 status, num_em_loop, alpha, lr, beta1, beta2, adam_eps, tau, lamda, C, K, D, cap,
                                 (cudaStream_t)stream);
+    }
 #endif
+    rc = mgp_em_plan(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop, stream);
+    if (rc != MGP_OK) return rc;
     if (em_fused_applies(K, D, cap)) {
         // one cluster of two CTAs per class runs the class's whole timeline (em_fused_kernel)
         const int kh = (K + 1) / 2 <= 3 ? 3 : ((K + 1) / 2 <= 5 ? 5 : 8);

@@ -40,6 +40,7 @@ constexpr int TAB = 256;
 
 struct EmTcParams {
     const float* xx;              // [C*cap] |x|^2 of the bank rows (shadow)
+    const float* bc;              // planner tables: [2 n] Adam bias corrections of steps step0+1.., then b1^i, b2^(i/2), b2^i for i <= n = L * n_active
     const int32_t* order;
     const int32_t* sched;
     float* mu;
@@ -57,14 +58,8 @@ struct EmTcParams {
 // (seen by thread 0), 4 epilogue done, 5 statistics MMAs issued, 6 loop tail entered, 7 loop tail done
 #define MGP_PROF(ctr, ph)                                                                          \
     do {                                                                                           \
-        if (prm.prof && c == prm.prof_class && (ctr) < 64) prm.prof[(ctr) * 8 + (ph)] = clock64();  \
+        if (prm.prof && blockIdx.x == prm.prof_class && (ctr) < 64) prm.prof[(ctr) * 8 + (ph)] = clock64();  \
     } while (0)
-
-// byte offset of element (row r < 16, col k) of a [16 x D] fp16 operand stored K-major SWIZZLE_128B as D/64 blocks of
-// [16 rows x 128 B]: 16-byte chunks XOR-ed with (row & 7)
-__device__ __forceinline__ uint32_t swz16(int r, int k) {
-    return (uint32_t)((k >> 6) * 2048 + r * 128 + (((((k & 63) >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
-}
 
 template <int D, int KT>
 __global__ void __launch_bounds__(256, (D == 128) ? 2 : 1)
@@ -74,6 +69,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     constexpr uint32_t X_BYTES = NCH * CH_BYTES;   // hi (lo follows)
     constexpr int DB = D / 128;                    // 128-wide d blocks (statistics accumulators)
     constexpr int OWN = D;                         // threads owning mean/moment elements: thread d <-> (k, d) for all k
+    constexpr int TMEM_COLS = (D == 128) ? 64 : 128;    // 32 (E-step: hi.hi + lo.hi | hi.lo) + DB * 32 (statistics)
     constexpr int ISSUER = 128;                    // the TMA / MMA issuing thread: lane 0 of warp 4 (warps 0-3 run the E-step epilogue)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -81,23 +77,25 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     uint8_t* bp = smem_raw + (base - raw);
     // carve-up (bytes from `base`)
     const uint32_t o_xh = 0, o_xl = X_BYTES;
-    const uint32_t o_ah = 2 * X_BYTES, o_al = o_ah + NCH * 2048;          // means operand [16 x D] hi / lo
-    const uint32_t o_rh = o_al + NCH * 2048, o_rl = o_rh + 4096;          // responsibilities [16 x 128 rows] hi / lo
-    const uint32_t o_mu = o_rl + 4096;                                    // fp32 means [KT][D]
-    const uint32_t o_misc = o_mu + KT * D * 4;
-    float* s_mu = reinterpret_cast<float*>(bp + o_mu);
+    // means operand A and responsibilities R: per 64-wide K chunk one [32 rows x 128 B] block, rows 0-15 = hi,
+    // rows 16-31 = lo, so ONE N = 32 MMA multiplies the row tile's hi half with both and an N = 16 MMA adds lo x hi
+    const uint32_t o_a = 2 * X_BYTES;                                     // [NCH][32][128 B]
+    const uint32_t o_r = o_a + NCH * 4096;                                // [2 (64-row chunks)][32][128 B]
+    const uint32_t o_misc = o_r + 8192;
     uint64_t* bars = reinterpret_cast<uint64_t*>(bp + o_misc);            // tma, estep, stats (+ TMEM slot)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
     float* s_e = reinterpret_cast<float*>(bars + 4);                      // [KT][KT]
     float* s_c = s_e + KT * KT;                                           // [TAB]
     float* s_d = s_c + TAB;                                               // [TAB]
-    float* s_red = s_d + TAB;                                             // [8][16]
-    float* s_w = s_red + 128;                                             // [16] w_k
+    float* s_red = s_d + TAB;                                             // [8] + [8][16]
+    float* s_w = s_red + 136;                                             // [16] w_k
     float* s_ls = s_w + 16;                                               // [16] sum_d (log(sigma+eps) + log(2pi)/2)
     float* s_pi = s_ls + 16;                                              // [16]
     float* s_cst = s_pi + 16;                                             // [16]
     float* s_s0 = s_cst + 16;                                             // [16]
-    float* s_misc = s_s0 + 16;                                            // [8]: tail c, tail d, adam step size, bc2 sqrt, scale
+    float* s_misc = s_s0 + 16;                                            // [8]: replay sums T1..T3, min d; operand scale; moment decays
+    constexpr int NPAIR = KT * (KT - 1) / 2;
+    float* s_pair = s_misc + 8;                                           // [8 warps][NPAIR] partial |mu_i - mu_j|^2
     const uint32_t bar_tma = smem_u32(bars), bar_e = bar_tma + 8, bar_s = bar_tma + 16;
 
     const int c = blockIdx.x;
@@ -107,9 +105,9 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     const int K = prm.K, cap = prm.cap, L = prm.num_em_loop, P = prm.C * K, KD = K * D;
     const AdamCfg& adam = prm.adam;
     const bool own = tid < OWN;
-    float* mu_c = prm.mu + (size_t)c * KD;
     const float* sg_c = prm.sigma + (size_t)c * KD;
 
+    if (tid == 0) MGP_PROF(63, 0);
     float p_[KT], m_[KT], v_[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
@@ -119,41 +117,79 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
             p_[k] = prm.mu[o]; m_[k] = prm.exp_avg[o]; v_[k] = prm.exp_avg_sq[o];
         }
     }
-    // `count` zero-gradient Adam steps first+1 .. first+count on the registers (em_common.cuh)
+    // `count` zero-gradient Adam steps first+1 .. first+count on the registers (em_common.cuh).  The per-step sum
+    //   p <- p - m0 * sum_s c_s / (a d_s + eps),   a = sqrt(v0),
+    // is evaluated through its expansion in eps / (a d_s) (< 1e-3 whenever a d_min > 1e3 eps, i.e. v0 > ~1e-10):
+    //   sum_s c_s / (a d_s + eps) = T1 / a - eps T2 / a^2 + eps^2 T3 / a^3 - ...,   Tj = sum_s c_s / d_s^j,
+    // three block-wide scalars per replay (truncation < 1e-9) instead of one reciprocal per (step, element); elements
+    // with a tiny second moment (a fresh optimiser) take the explicit loop.
+    // The step-dependent factors come from tables the planner wrote once for the whole launch (em.cu em_plan_kernel):
+    //   bc[2i] = lr / (1 - b1^t), bc[2i+1] = sqrt(1 - b2^t), t = step0 + 1 + i;   B1[n] = b1^n, B2H[n] = b2^(n/2), B2[n] = b2^n
+    // so that c_s = bc0[t] B1[s], d_s = B2H[s] / bc1[t]: no transcendental is evaluated per class.
+    const int n_steps = L * n_active;
+    const float* t_b1 = prm.bc + 2 * n_steps;
+    const float* t_b2h = t_b1 + (n_steps + 1);
+    const float* t_b2 = t_b2h + (n_steps + 1);
     auto replay = [&](int first, int count) {
         if (count <= 0) return;
-        float a_[KT];
+        const int ns = replay_explicit_steps(count, first, (float)adam.beta1);
+        const bool tail = count > ns;
+        const int i0 = first - step0;                       // table index of step first+1
+        __syncthreads();
+        if (warp == 0) {
+            double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            float dmin = INFINITY;
+            for (int s = lane + 1; s <= ns + (tail ? 1 : 0); s += 32) {
+                float cs, ds;
+                if (s <= ns) {
+                    cs = __ldg(prm.bc + 2 * (i0 + s - 1)) * __ldg(t_b1 + s);
+                    ds = __ldg(t_b2h + s) / __ldg(prm.bc + 2 * (i0 + s - 1) + 1);
+                } else {                                    // steps ns+1 .. count as one geometric term (em_common.cuh)
+                    const float geo = __ldg(t_b1 + ns + 1) * (1.0f - __ldg(t_b1 + (count - ns))) / (float)(1.0 - adam.beta1);
+                    const int ss = min(count, ns + 1 + (int)(adam.beta1 / (1.0 - adam.beta1)));
+                    cs = __ldg(prm.bc + 2 * (i0 + ns)) * geo;
+                    ds = __ldg(t_b2h + ss) / __ldg(prm.bc + 2 * (i0 + ss - 1) + 1);
+                }
+                const double c = (double)cs, r = 1.0 / (double)ds;
+                t1 += c * r; t2 += c * r * r; t3 += c * r * r * r;
+                dmin = fminf(dmin, ds);
+            }
 #pragma unroll
-        for (int k = 0; k < KT; ++k) a_[k] = sqrtf(v_[k]);
-        const int count_p = replay_explicit_steps(count, first, (float)adam.beta1);
-        for (int s0 = 0; s0 < count_p; s0 += TAB) {
-            const int ns = min(TAB, count_p - s0);
-            __syncthreads();
-            for (int s = tid; s < ns; s += 256) replay_coeffs(adam, first, s0 + s + 1, s_c[s], s_d[s]);
-            if (tid == 255 && s0 + TAB >= count_p && count > count_p) replay_tail(adam, first, count_p, count, s_misc[0], s_misc[1]);
-            __syncthreads();
-            if (own) {
-                for (int s = 0; s < ns; ++s) {
-                    const float cs = -s_c[s], ds = s_d[s];
+            for (int o = 16; o > 0; o >>= 1) {
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+                t3 += __shfl_xor_sync(0xffffffffu, t3, o);
+                dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+            }
+            if (lane == 0) { s_misc[0] = (float)t1; s_misc[1] = (float)t2; s_misc[2] = (float)t3; s_misc[3] = dmin; }
+        }
+        __syncthreads();
+        if (own) {
+            const float T1 = s_misc[0], T2 = s_misc[1], T3 = s_misc[2], dmin = s_misc[3];
 #pragma unroll
-                    for (int k = 0; k < KT; ++k) {
-                        float rc;
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[k], ds, adam.epsf)));
-                        p_[k] = fmaf(cs * m_[k], rc, p_[k]);
+            for (int k = 0; k < KT; ++k) {
+                const float a = sqrtf(v_[k]);
+                if (a * dmin > 1000.0f * adam.epsf) {
+                    const float inv = 1.0f / a;
+                    const float e = adam.epsf * inv;
+                    p_[k] = fmaf(-m_[k] * inv, fmaf(-e, fmaf(-e, T3, T2), T1), p_[k]);
+                } else if (m_[k] != 0.f) {                  // tiny second moment (fresh optimiser): term by term
+                    for (int s = 1; s <= ns; ++s) {
+                        const float cs = __ldg(prm.bc + 2 * (i0 + s - 1)) * __ldg(t_b1 + s);
+                        const float ds = __ldg(t_b2h + s) / __ldg(prm.bc + 2 * (i0 + s - 1) + 1);
+                        p_[k] = fmaf(-cs * m_[k], 1.0f / fmaf(a, ds, adam.epsf), p_[k]);
+                    }
+                    if (tail) {
+                        const float geo = __ldg(t_b1 + ns + 1) * (1.0f - __ldg(t_b1 + (count - ns))) / (float)(1.0 - adam.beta1);
+                        const int ss = min(count, ns + 1 + (int)(adam.beta1 / (1.0 - adam.beta1)));
+                        const float cs = __ldg(prm.bc + 2 * (i0 + ns)) * geo;
+                        const float ds = __ldg(t_b2h + ss) / __ldg(prm.bc + 2 * (i0 + ss - 1) + 1);
+                        p_[k] = fmaf(-cs * m_[k], 1.0f / fmaf(a, ds, adam.epsf), p_[k]);
                     }
                 }
             }
         }
-        if (count > count_p && own) {
-            const float cs = -s_misc[0], ds = s_misc[1];
-#pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                float rc;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(a_[k], ds, adam.epsf)));
-                p_[k] = fmaf(cs * m_[k], rc, p_[k]);
-            }
-        }
-        const float mdec = (float)pow(adam.beta1, (double)count), vdec = (float)pow(adam.beta2, (double)count);
+        const float mdec = __ldg(t_b1 + count), vdec = __ldg(t_b2 + count);   // the moments decay by the full count
 #pragma unroll
         for (int k = 0; k < KT; ++k) { m_[k] *= mdec; v_[k] *= vdec; }
     };
@@ -173,6 +209,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         return;
     }
 
+    if (tid == 0) MGP_PROF(63, 1);
     // ---- set-up: barriers, TMEM, sigma-derived constants, zeroed operand tiles
     if (tid == 0) {
         mbar_init(bar_tma, 1);
@@ -181,13 +218,14 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     bool same = true;
     for (int i = tid; i < KD; i += 256) same = same && (sg_c[i] == sg_c[(i / D) * D]);
-    for (uint32_t i = tid * 16u; i < 2u * NCH * 2048u + 8192u; i += 256u * 16u)        // A hi/lo and R hi/lo: rows >= K stay zero
-        *reinterpret_cast<uint4*>(bp + o_ah + i) = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid * 16u; i < NCH * 4096u + 8192u; i += 256u * 16u)             // A and R blocks: rows >= K stay zero
+        *reinterpret_cast<uint4*>(bp + o_a + i) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < KT * KT; i += 256) s_e[i] = 0.f;
     if (tid < 16) {
         float w = 0.f, ls = 0.f, pi = 0.f;
         if (tid < K) {
@@ -204,73 +242,103 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
     if (!iso) {                                      // the host promised isotropic sigma: flag it, leave the class untouched
         if (tid == 0) atomicExch(prm.status, 1);
-        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
         return;
     }
+    if (tid == 0) MGP_PROF(63, 2);
     replay(step0, L * ord);
+    if (tid == 0) MGP_PROF(63, 3);
 
     const int ntiles = (cap + TR - 1) / TR;
     const float n_rows = (float)cap;
     const float inv_den = 1.0f / (1.0f + (float)K * prm.alpha);
     const float div_scale = -4.0f * prm.lamda / ((float)K * (float)(K - 1));
-    const uint32_t idesc_e = umma_idesc_f16(TR, NK, 0, 0);          // E-step: A = X (K-major), B = means (K-major)
-    const uint32_t idesc_s = umma_idesc_f16(128, NK, 1, 0);         // statistics: A = X^T (MN-major), B = R (K-major)
-    const uint32_t d_e = tmem_base;                                  // [128 rows x 16]
-    const uint32_t d_s = tmem_base + 16;                             // DB x [128 d x 16]
+    // E-step: A = X (K-major), B = [means hi ; means lo] (K-major): N = 32 with X hi, N = 16 (hi only) with X lo
+    const uint32_t idesc_e32 = umma_idesc_f16(TR, 2 * NK, 0, 0), idesc_e16 = umma_idesc_f16(TR, NK, 0, 0);
+    // statistics: A = X^T (MN-major), B = [R hi ; R lo] (K-major)
+    const uint32_t idesc_s32 = umma_idesc_f16(128, 2 * NK, 1, 0), idesc_s16 = umma_idesc_f16(128, NK, 1, 0);
+    const uint32_t d_e = tmem_base;                                  // [128 rows x (16 hi.hi + lo.hi | 16 hi.lo)]
+    const uint32_t d_s = tmem_base + 32;                             // DB x [128 d x 32], same column split
     uint32_t tile_ctr = 0;                                           // tiles issued so far (mbarrier phases)
 
-    for (int loop = 0; loop < L; ++loop) {
-        // ---- means operand, |mu_k|^2, diversity kernel from the current means
-        float amax = 0.f;
+    auto load_tile = [&](int t) {                                    // issuer only: one 128-row tile, hi + lo, into the X buffer
+        mbar_expect_tx(bar_tma, 2 * X_BYTES);
+        const int row0 = c * cap + t * TR;
 #pragma unroll
-        for (int k = 0; k < KT; ++k)
+        for (int ch = 0; ch < NCH; ++ch) {
+            tma_load_2d(base + o_xh + ch * CH_BYTES, &map_h, ch * 64, row0, bar_tma);
+            tma_load_2d(base + o_xl + ch * CH_BYTES, &map_l, ch * 64, row0, bar_tma);
+        }
+    };
+    for (int loop = 0; loop < L; ++loop) {
+        // ---- means operand, |mu_k|^2, diversity kernel from the current means (all from the owners' registers)
+        float amax = 0.f;
+        float mmp[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            mmp[k] = 0.f;
             if (own && k < K) {
-                s_mu[k * D + tid] = p_[k];
                 amax = fmaxf(amax, fabsf(2.0f * s_w[k] * p_[k]));
+                mmp[k] = p_[k] * p_[k];
             }
+        }
         amax = warp_max(amax);
-        if (lane == 0) s_red[warp] = amax;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) mmp[k] = warp_sum(mmp[k]);
+        if (lane == 0) {
+            s_red[warp] = amax;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) s_red[8 + warp * 16 + k] = mmp[k];
+        }
+        {   // |mu_i - mu_j|^2 (ref utils/helpers.py:13-14): this thread's dimension, reduced over the warp, i < j
+            int pi = 0;
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+#pragma unroll
+                for (int j = i + 1; j < KT; ++j, ++pi) {
+                    const float df = (own && j < K) ? p_[i] - p_[j] : 0.f;
+                    const float t = warp_sum(df * df);
+                    if (lane == 0) s_pair[warp * NPAIR + pi] = t;
+                }
+        }
         __syncthreads();
-        if (tid == 0) {
+        float a_scale;
+        {
             float mx = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, s_red[w8]);
             int ex = 0;
             if (mx > 0.f) frexpf(mx, &ex);
-            s_misc[4] = ldexpf(1.0f, 8 - ex);                        // max |a| * scale in [128, 256)
+            a_scale = ldexpf(1.0f, 8 - ex);                          // max |a| * scale in [128, 256)
         }
-        __syncthreads();
-        const float a_scale = s_misc[4];
+        if (tid < K) {
+            float mm = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) mm += s_red[8 + w8 * 16 + tid];
+            s_cst[tid] = -s_ls[tid] + logf(s_pi[tid] + EM_EPS) - 0.5f * s_w[tid] * mm;   // ref :316, :323-336
+        }
+        if (tid >= 32 && tid < 32 + NPAIR) {                         // exp(-|mu_i - mu_j|^2), ref model.py:390-392
+            const int pr = tid - 32;
+            int i = 0, rem = pr;
+            while (rem >= KT - 1 - i) { rem -= KT - 1 - i; ++i; }
+            const int j = i + 1 + rem;
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < OWN / 32; ++w8) t += s_pair[w8 * NPAIR + pr];
+            const float e = (j < K) ? expf(-t) : 0.f;
+            s_e[i * KT + j] = e;
+            s_e[j * KT + i] = e;
+        }
 #pragma unroll
         for (int k = 0; k < KT; ++k)
             if (own && k < K) {
                 const float a = -2.0f * s_w[k] * p_[k] * a_scale;
                 const __half h = __float2half_rn(a);
-                const uint32_t off = swz16(k, tid);
-                *reinterpret_cast<__half*>(bp + o_ah + off) = h;
-                *reinterpret_cast<__half*>(bp + o_al + off) = __float2half_rn(a - __half2float(h));
+                const uint32_t off = (uint32_t)(tid >> 6) * 4096u + (uint32_t)k * 128u +
+                                     (uint32_t)(((((tid & 63) >> 3) ^ (k & 7)) & 7) << 4) + (uint32_t)(tid & 7) * 2u;
+                *reinterpret_cast<__half*>(bp + o_a + off) = h;                                   // row k      (hi)
+                *reinterpret_cast<__half*>(bp + o_a + off + 2048u) = __float2half_rn(a - __half2float(h));   // row 16 + k (lo): same swizzle phase
             }
-        for (int k = warp; k < K; k += 8) {                          // |mu_k|^2 and the per-component constant
-            float mm = 0.f;
-            for (int d = lane; d < D; d += 32) mm = fmaf(s_mu[k * D + d], s_mu[k * D + d], mm);
-            mm = warp_sum(mm);
-            if (lane == 0) s_cst[k] = -s_ls[k] + logf(s_pi[k] + EM_EPS) - 0.5f * s_w[k] * mm;   // ref :316, :323-336
-        }
-        for (int pr = warp; pr < K * K; pr += 8) {                   // ref utils/helpers.py:13-14, model.py:390-392
-            const int i = pr / K, j = pr - i * K;
-            float t = 0.f;
-            for (int d = lane; d < D; d += 32) {
-                const float df = s_mu[i * D + d] - s_mu[j * D + d];
-                t = fmaf(df, df, t);
-            }
-            t = warp_sum(t);
-            if (lane == 0) s_e[i * KT + j] = (i == j) ? 0.f : expf(-t);
-        }
-        if (tid == 0) {
-            const double stp = (double)(step0 + L * ord + loop + 1);
-            s_misc[2] = (float)(adam.lr / (1.0 - pow(adam.beta1, stp)));
-            s_misc[3] = (float)sqrt(1.0 - pow(adam.beta2, stp));
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // operand stores -> visible to the MMA (async proxy)
         __syncthreads();
 
@@ -282,28 +350,21 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         for (int t = 0; t < ntiles; ++t, ++tile_ctr) {
             const uint32_t par = tile_ctr & 1u;
             if (tid == ISSUER) {
-                if (tile_ctr > 0) mbar_wait(bar_s, (tile_ctr - 1) & 1u);     // previous statistics MMAs have read X and R
                 MGP_PROF(tile_ctr, 0);
-                mbar_expect_tx(bar_tma, 2 * X_BYTES);
-                const int row0 = c * cap + t * TR;
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    tma_load_2d(base + o_xh + ch * CH_BYTES, &map_h, ch * 64, row0, bar_tma);
-                    tma_load_2d(base + o_xl + ch * CH_BYTES, &map_l, ch * 64, row0, bar_tma);
+                if (!(t == 0 && loop > 0)) {                                 // (a loop's first tile was prefetched by the previous loop)
+                    if (tile_ctr > 0) mbar_wait(bar_s, (tile_ctr - 1) & 1u); // previous statistics MMAs have read X and R
+                    load_tile(t);
                 }
                 mbar_wait(bar_tma, par);
                 MGP_PROF(tile_ctr, 1);
                 tc_fence_after();
-                // E-step: D_e[row, k] = sum_d X[row, d] A[k, d]   (3 passes: hi.hi + lo.hi + hi.lo)
+                // E-step: D_e[row, 0:32] = X_hi . [A_hi ; A_lo]^T (N = 32);  D_e[row, 0:16] += X_lo . A_hi^T (N = 16)
 #pragma unroll
                 for (int ks = 0; ks < D / 16; ++ks) {
                     const uint32_t xo = (uint32_t)(ks >> 2) * CH_BYTES + (uint32_t)(ks & 3) * 32u;
-                    const uint32_t ao = (uint32_t)(ks >> 2) * 2048u + (uint32_t)(ks & 3) * 32u;
-                    const uint64_t xh = umma_desc(base + o_xh + xo), xl = umma_desc(base + o_xl + xo);
-                    const uint64_t ah = umma_desc(base + o_ah + ao), al = umma_desc(base + o_al + ao);
-                    tc_mma_f16(d_e, xh, ah, idesc_e, ks != 0);
-                    tc_mma_f16(d_e, xl, ah, idesc_e, 1u);
-                    tc_mma_f16(d_e, xh, al, idesc_e, 1u);
+                    const uint64_t bd = umma_desc(base + o_a + (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u);
+                    tc_mma_f16(d_e, umma_desc(base + o_xh + xo), bd, idesc_e32, ks != 0);
+                    tc_mma_f16(d_e, umma_desc(base + o_xl + xo), bd, idesc_e16, 1u);      // lo.hi adds onto the hi.hi columns
                 }
                 tc_commit(bar_e);
                 MGP_PROF(tile_ctr, 2);
@@ -316,13 +377,15 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                 mbar_wait(bar_e, par);
                 if (tid == 0) MGP_PROF(tile_ctr, 3);
                 tc_fence_after();
-                uint32_t q[16];
+                uint32_t q[16], q1[16];
                 tmem_ld16(d_e + ((uint32_t)(warp * 32) << 16), q);
+                tmem_ld16(d_e + 16 + ((uint32_t)(warp * 32) << 16), q1);
                 tmem_ld_wait();
                 float wl[KT], mx = -INFINITY;
 #pragma unroll
                 for (int k = 0; k < KT; ++k) {
-                    const float qq = fmaf(s_w[k], xxv, __uint_as_float(q[k]) * inv_a);
+                    const float acc = __uint_as_float(q[k]) + __uint_as_float(q1[k]);
+                    const float qq = fmaf(s_w[k], xxv, acc * inv_a);
                     wl[k] = (k < K) ? s_cst[k] - 0.5f * qq : -INFINITY;                 // lp + log(pi + eps)  (ref :316)
                     mx = fmaxf(mx, wl[k]);
                 }
@@ -333,7 +396,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                     se += wl[k];
                 }
                 const float inv_se = 1.0f / se;
-                const uint32_t rbase = (uint32_t)(tid >> 6) * 2048u + (uint32_t)(tid & 7) * 2u;
+                const uint32_t rbase = (uint32_t)(tid >> 6) * 4096u + (uint32_t)(tid & 7) * 2u;
                 const int c16 = (tid & 63) >> 3;
 #pragma unroll
                 for (int k = 0; k < KT; ++k)
@@ -343,8 +406,8 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
                         const float rs = r * SR;
                         const __half h = __float2half_rn(rs);
                         const uint32_t off = rbase + (uint32_t)k * 128u + (uint32_t)(((c16 ^ (k & 7)) & 7) << 4);
-                        *reinterpret_cast<__half*>(bp + o_rh + off) = h;
-                        *reinterpret_cast<__half*>(bp + o_rl + off) = __float2half_rn(rs - __half2float(h));
+                        *reinterpret_cast<__half*>(bp + o_r + off) = h;                                           // row k
+                        *reinterpret_cast<__half*>(bp + o_r + off + 2048u) = __float2half_rn(rs - __half2float(h));   // row 16 + k
                     }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tc_fence_before();
@@ -353,19 +416,15 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
             __syncthreads();
             if (tid == ISSUER) {
                 tc_fence_after();
-                // statistics: D_s[d, k] += sum_row X[row, d] R[row, k]
+                // statistics: D_s[d, 0:32] += X_hi^T . [R_hi ; R_lo] (N = 32);  D_s[d, 0:16] += X_lo^T . R_hi (N = 16)
 #pragma unroll
                 for (int db = 0; db < DB; ++db) {
 #pragma unroll
                     for (int ks = 0; ks < TR / 16; ++ks) {
                         const uint32_t xo = (uint32_t)db * 2u * CH_BYTES + (uint32_t)ks * 2048u;   // 16 rows x 128 B
-                        const uint32_t ro = (uint32_t)(ks >> 2) * 2048u + (uint32_t)(ks & 3) * 32u;
-                        const uint64_t xh = umma_desc_mn(base + o_xh + xo, CH_BYTES, 1024u);
-                        const uint64_t xl = umma_desc_mn(base + o_xl + xo, CH_BYTES, 1024u);
-                        const uint64_t rh = umma_desc(base + o_rh + ro), rl = umma_desc(base + o_rl + ro);
-                        tc_mma_f16(d_s + db * 16, xh, rh, idesc_s, (t | ks) != 0);
-                        tc_mma_f16(d_s + db * 16, xl, rh, idesc_s, 1u);
-                        tc_mma_f16(d_s + db * 16, xh, rl, idesc_s, 1u);
+                        const uint64_t bd = umma_desc(base + o_r + (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u);
+                        tc_mma_f16(d_s + db * 32, umma_desc_mn(base + o_xh + xo, CH_BYTES, 1024u), bd, idesc_s32, (t | ks) != 0);
+                        tc_mma_f16(d_s + db * 32, umma_desc_mn(base + o_xl + xo, CH_BYTES, 1024u), bd, idesc_s16, 1u);
                     }
                 }
                 tc_commit(bar_s);
@@ -373,6 +432,10 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
             }
         }
         if (tid == 0) MGP_PROF(tile_ctr - 1, 6);
+        if (tid == ISSUER && loop + 1 < L) {          // the next loop starts on the same rows: fetch its first tile under the tail
+            mbar_wait(bar_s, (tile_ctr - 1) & 1u);
+            load_tile(0);
+        }
         // ---- S0 over the class, S1 from TMEM
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
@@ -384,55 +447,68 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         tc_fence_after();
         __syncthreads();
         if (tid < K) s_s0[tid] = (s_red[tid] + s_red[16 + tid]) + (s_red[32 + tid] + s_red[48 + tid]);
-        uint32_t sacc[16];
+        uint32_t sacc[16], sacc1[16];
         if (own) {
-            tmem_ld16(d_s + (uint32_t)(tid >> 7) * 16u + ((uint32_t)((warp & 3) * 32) << 16), sacc);
+            const uint32_t ta = d_s + (uint32_t)(tid >> 7) * 32u + ((uint32_t)((warp & 3) * 32) << 16);
+            tmem_ld16(ta, sacc);
+            tmem_ld16(ta + 16, sacc1);
             tmem_ld_wait();
         }
         tc_fence_before();
         __syncthreads();
         // ---- gradient + diversity + Adam on the owned elements (ref model.py:385-397)
         if (own) {
-            const float step_size = s_misc[2], bc2_sqrt = s_misc[3];
+            const int sidx = L * ord + loop;                                  // this Adam step's bias corrections
+            const float step_size = __ldg(prm.bc + 2 * sidx), bc2_sqrt = __ldg(prm.bc + 2 * sidx + 1);
+            float newp[KT];
 #pragma unroll
-            for (int k = 0; k < KT; ++k)
+            for (int k = 0; k < KT; ++k) {
+                newp[k] = p_[k];
                 if (k < K) {
                     const float muv = p_[k];
-                    const float s1 = __uint_as_float(sacc[k]) * (1.0f / (SX * SR));
+                    const float s1 = (__uint_as_float(sacc[k]) + __uint_as_float(sacc1[k])) * (1.0f / (SX * SR));
                     float g = -(s1 - muv * s_s0[k]) * s_w[k] / n_rows;
                     float esum = 0.f, emu = 0.f;
-                    for (int j = 0; j < K; ++j) {
-                        const float e = s_e[k * KT + j];
-                        esum += e;
-                        emu = fmaf(e, s_mu[j * D + tid], emu);
-                    }
+#pragma unroll
+                    for (int j = 0; j < KT; ++j)
+                        if (j < K) {
+                            const float e = s_e[k * KT + j];                  // broadcast
+                            esum += e;
+                            emu = fmaf(e, p_[j], emu);                        // mu_j[d] is this thread's own register
+                        }
                     g += div_scale * (esum * muv - emu);
                     const float mm = m_[k] + (g - m_[k]) * adam.omb1;             // torch.optim.Adam (_single_tensor_adam)
                     const float vv = v_[k] * adam.b2f + adam.omb2 * g * g;
                     const float denom = sqrtf(vv) / bc2_sqrt + adam.epsf;
-                    p_[k] = muv - step_size * (mm / denom);
+                    newp[k] = muv - step_size * (mm / denom);
                     m_[k] = mm; v_[k] = vv;
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < KT; ++k) p_[k] = newp[k];
         }
         __syncthreads();                                              // every reader of s_mu / s_s0 is done
         if (tid < K) s_pi[tid] = prm.tau * s_pi[tid] + prm.omtau * ((s_s0[tid] + EM_EPS) / n_rows);   // ref :385, :399, :297
         if (tid == 0) MGP_PROF(tile_ctr - 1, 7);
     }
+    if (tid == 0) MGP_PROF(63, 4);
     replay(step0 + L * (ord + 1), L * (n_active - ord - 1));
+    if (tid == 0) MGP_PROF(63, 5);
     write_back();
     if (tid < K) prm.weight[(size_t)c * P + (size_t)c * K + tid] = s_pi[tid];
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
+    if (tid == 0) MGP_PROF(63, 6);
 }
 
 template <int D>
 size_t em_tc_smem(int kt) {
-    return 1024 + 2 * (size_t)(D / 64) * TR * 128 + 2 * (size_t)(D / 64) * 2048 + 8192 + (size_t)kt * D * 4 +
-           ((size_t)kt * kt + 2 * TAB + 128 + 6 * 16 + 8) * 4 + 64;
+    return 1024 + 2 * (size_t)(D / 64) * TR * 128 + (size_t)(D / 64) * 4096 + 8192 +
+           ((size_t)kt * kt + 2 * TAB + 136 + 6 * 16 + 8 + 8 * (size_t)(kt * (kt - 1) / 2)) * 4 + 64;
 }
 
 }  // namespace
@@ -445,7 +521,7 @@ bool mgp_em_tc_supported(int K, int D, int cap) {
     return K >= 2 && K <= 16 && (D == 128 || D == 256) && cap >= 1 && get_encode() != nullptr;
 }
 
-int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* shadow_xx, const int32_t* order,
+int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* shadow_xx, const float* bias_corr, const int32_t* order,
                      const int32_t* sched, float* mu, const float* sigma, float* weight, float* exp_avg, float* exp_avg_sq,
                      int* status, int num_em_loop, float alpha, double lr, double beta1, double beta2, double adam_eps,
                      double tau, float lamda, int C, int K, int D, int cap, cudaStream_t st) {
@@ -453,7 +529,7 @@ int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* sh
     const uint64_t rows = (uint64_t)C * cap;
     if (!make_map_f16(&mh, shadow_h, rows, D, TR) || !make_map_f16(&ml, shadow_l, rows, D, TR)) return MGP_ERR_UNSUPPORTED;
     EmTcParams prm;
-    prm.xx = shadow_xx; prm.order = order; prm.sched = sched; prm.mu = mu; prm.sigma = sigma; prm.weight = weight;
+    prm.xx = shadow_xx; prm.bc = bias_corr; prm.order = order; prm.sched = sched; prm.mu = mu; prm.sigma = sigma; prm.weight = weight;
     prm.exp_avg = exp_avg; prm.exp_avg_sq = exp_avg_sq; prm.status = status;
     prm.adam = make_adam(lr, beta1, beta2, adam_eps);
     prm.alpha = alpha; prm.tau = (float)tau; prm.omtau = (float)(1.0 - tau); prm.lamda = lamda;

@@ -32,7 +32,7 @@ for cls in (3, 120):
     t = buf.cpu().view(64, 8).double() / mhz          # microseconds
     t0 = t[0, 0]
     print("class %d (SM clock %.0f MHz): tile: TMA-wait E-issue E-done epilogue S-issue | tile total; * = loop tail" % (cls, mhz))
-    for i in range(64):
+    for i in range(63):
         if t[i, 0] == 0:
             break
         r = t[i]
@@ -40,4 +40,7 @@ for cls in (3, 120):
         tail = "  * tail %.2f us (gather S0/S1 + update)" % (r[7] - r[6]) if r[6] > 0 else ""
         print("%2d @%7.2f: %5.2f %5.2f %5.2f %5.2f %5.2f | %5.2f%s" % (i, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2],
                                                                      r[4] - r[3], r[5] - r[4], nxt - r[0], tail))
+    m = t[63]
+    print("   entry->state loaded %.2f | set-up %.2f | lead replay %.2f | EM loops %.2f | trail replay %.2f | write-back+dealloc %.2f | total %.2f us"
+          % (m[1] - m[0], m[2] - m[1], m[3] - m[2], m[4] - m[3], m[5] - m[4], m[6] - m[5], m[6] - m[0]))
 net.sync_optimizer_state()

@@ -59,6 +59,8 @@ const char* mgp_error_string(int code);
 /* 1 if the library was built with the sm_100a tcgen05 kernels */
 int mgp_has_tensor_core_path(void);
 /* Process-wide test / diagnosis switches (not part of the reference surface; the defaults are the product path).
+ * key "tc_z": 1 (default; 0 if MGP_TC_NO_Z is set) = the [N,P] log-likelihood with isotropic sigma and D <= 128 takes the
+ * TMEM-resident kernel (csrc/logprob_tcz.cu), 0 = always csrc/logprob_tc.cu;
  * key "em_tc": 1 (default; 0 if MGP_EM_NO_TC is set) = mgp_update_gmm may take the tensor-core kernel;
  * key "em_fused": 1 (default; 0 if MGP_EM_UNFUSED is set in the environment) = mgp_update_gmm runs the single
  * cluster launch where the shape allows, 0 = always the multi-launch path (identical arithmetic, used by the

@@ -39,6 +39,11 @@ extern "C" int mgp_debug_set_ptr(const char* key, void* p, int arg) {
 #endif
     return MGP_ERR_INVALID;
 }
+int g_mgp_tc_z = -1;
+int mgp_opt_tc_z() {
+    if (g_mgp_tc_z < 0) g_mgp_tc_z = getenv("MGP_TC_NO_Z") ? 0 : 1;
+    return g_mgp_tc_z;
+}
 int g_mgp_em_tc = -1;
 int mgp_opt_em_tc() {
     if (g_mgp_em_tc < 0) g_mgp_em_tc = getenv("MGP_EM_NO_TC") ? 0 : 1;
@@ -46,6 +51,11 @@ int mgp_opt_em_tc() {
 }
 extern "C" int mgp_set_option(const char* key, int value) {
     if (!key) return MGP_ERR_INVALID;
+    if (strcmp(key, "tc_z") == 0) {
+        const int prev = mgp_opt_tc_z();
+        g_mgp_tc_z = value ? 1 : 0;
+        return prev;
+    }
     if (strcmp(key, "em_tc") == 0) {
         const int prev = mgp_opt_em_tc();
         g_mgp_em_tc = value ? 1 : 0;

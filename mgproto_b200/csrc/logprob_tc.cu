@@ -54,6 +54,7 @@ __global__ void tc_proto_prep_kernel(const float* __restrict__ mu, const float* 
                                      float eps_log, __half* __restrict__ bh, __half* __restrict__ bl,
                                      float* __restrict__ e0, float* __restrict__ e1, float* __restrict__ e2,
                                      int* __restrict__ noniso, int P, int D) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a dependent launched programmatically may start its prologue
     const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (p >= P) return;
@@ -585,6 +586,12 @@ WsLayout ws_layout(long long N, int P, int D) {
 
 }  // namespace
 
+// logprob_tcz.cu: [N,P] output, isotropic sigma, D <= 128: patch tile resident in TMEM, x split fused
+bool mgp_logprob_tcz_supported(int P, int D);
+int mgp_logprob_tcz_launch(const float* xhat, const void* bh, const void* bl, const float* e0, const float* e1,
+                           const float* e2, const int* noniso, float* out, long long N, int P, int D, cudaStream_t st);
+int mgp_opt_tc_z();   // abi.cu
+
 bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D, int assume_iso) {
     (void)layout;
     // K blocks of 64; the x tile (128 patches x K x 4 B, K = 2D when some sigma is anisotropic) must fit in
@@ -613,13 +620,18 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     float* sn = reinterpret_cast<float*>(wsb + w.sn);
     int* flag = reinterpret_cast<int*>(wsb + w.flag);
 
+    // [N,P] with isotropic sigma (asserted by the caller) and D <= 128: the TMEM-resident kernel reads fp32 x itself
+    const bool use_z = (layout == MGP_OUT_LOGP_NP) && assume_iso && mgp_opt_tc_z() && mgp_logprob_tcz_supported(P, D);
     if (!reuse_operands) {
         MGP_CUDA(cudaMemsetAsync(flag, 0, 4, st));
         tc_proto_prep_kernel<<<(P + 7) / 8, 256, 0, st>>>(mu, sigma, eps, eps_log, bh, bl, e0, e1, e2, flag, P, D);
         MGP_CHECK_LAUNCH();
-        tc_x_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(xhat, ah, al, sn, flag, (int)N, D);
-        MGP_CHECK_LAUNCH();
+        if (!use_z) {
+            tc_x_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(xhat, ah, al, sn, flag, (int)N, D);
+            MGP_CHECK_LAUNCH();
+        }
     }
+    if (use_z) return mgp_logprob_tcz_launch(xhat, bh, bl, e0, e1, e2, flag, out, N, P, D, st);
 
     CUtensorMap mxh, mxl, mph, mpl;
     CUtensorMap mout;

@@ -156,9 +156,14 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
         raise RuntimeError("mgproto_b200: out has the wrong shape")
     lib = _lib.load()
     m = _math(math)
-    if m == MGP_MATH_AUTO and D > 128:
-        # wider features only fit the tensor-core tiles when sigma is isotropic: decided on the host (cached)
-        m = MGP_MATH_TC_ISO if (D == 256 and sigma_is_isotropic(sg)) else MGP_MATH_FP32
+    if m == MGP_MATH_AUTO:
+        # one cached host check (sigma never changes in the reference's loop): isotropic sigma lets the [N,P] layout
+        # take the TMEM-resident kernel with the fused operand split (D <= 128) and D = 256 fit the tensor-core tiles
+        iso = sigma_is_isotropic(sg)
+        if D > 128:
+            m = MGP_MATH_TC_ISO if (D == 256 and iso) else MGP_MATH_FP32
+        elif iso and D in (64, 128):
+            m = MGP_MATH_TC_ISO
     nbytes = lib.mgp_logprob_ws_bytes(B_, HW_, P, D, m)
     if ws is None:
         ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)

@@ -339,6 +339,32 @@ def test_logprob_tc_vs_fp32(shape, sigma_mode):
         torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 if layout != 2 else 1e-12)
 
 
+@pytest.mark.parametrize("shape", [(3, 49, 130, 64), (5, 196, 2000, 128), (2, 200, 257, 128), (1, 7, 5, 128), (9, 196, 1000, 64)])
+def test_logprob_tmem_resident_kernel_vs_fp64(shape):
+    """compute_log_prob's [N,P] kernel with the patch tile resident in tensor memory and the fp16 hi/lo split fused
+    (csrc/logprob_tcz.cu; taken by math='auto' when sigma is isotropic, D <= 128): ragged tiles on both sides, against
+    float64 and against the kernel that splits x in a pre-pass (csrc/logprob_tc.cu)."""
+    from mgproto_b200 import ops, _lib
+    lib = _lib.load()
+    if not lib.mgp_has_tensor_core_path():
+        pytest.skip("library built without the tcgen05 path")
+    B, HW, P, D = shape
+    g = torch.Generator().manual_seed(11)
+    x = F.normalize(torch.randn(B * HW, D, generator=g), dim=1).to(_dev())
+    mu = F.normalize(torch.rand(P, D, generator=g), dim=1).to(_dev())
+    sg = (0.25 + 0.5 * torch.rand(P, 1, generator=g)).expand(P, D).contiguous().to(_dev())
+    ref64 = (-0.5 * D * np.log(2 * np.pi) - sg.double().log().sum(1)[None, :]
+             - 0.5 * (((x.double()[:, None, :] - mu.double()[None]) / sg.double()[None]) ** 2).sum(-1))
+    a = ops.logprob(x, mu, sg, 0, math="auto")
+    prev = lib.mgp_set_option(b"tc_z", 0)
+    try:
+        b = ops.logprob(x, mu, sg, 0, math="auto")
+    finally:
+        lib.mgp_set_option(b"tc_z", prev)
+    torch.testing.assert_close(a.double(), ref64, rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5)
+
+
 def test_logprob_tc_baseline_size_properties():
     """cfg2 size (B=256, P=2000, D=128): KA1 identity on a strided sample + exact agreement of the
     three output layouts with each other (size-independent properties; no CPU oracle at this size)."""
@@ -354,6 +380,9 @@ def test_logprob_tc_baseline_size_properties():
     rows = torch.arange(0, B * HW, 97, device=_dev())
     ref = -np.pi * ((x[rows].double()[:, None, :] - mu.double()[None]) ** 2).sum(-1)       # KA1
     torch.testing.assert_close(lp[rows].double(), ref, rtol=1e-5, atol=2e-5)
+    lpz = ops.logprob(x, mu, sg, 0, math="auto")                                           # TMEM-resident kernel
+    torch.testing.assert_close(lpz[rows].double(), ref, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(lpz, lp, rtol=2e-5, atol=2e-5)
     lp_b = ops.logprob(x, mu, sg, 1, B=B, HW=HW, math="tc")
     assert torch.equal(lp_b, lp.view(B, HW, P).permute(0, 2, 1).contiguous())
     assert torch.isfinite(lp).all()

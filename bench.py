@@ -524,35 +524,41 @@ def main():
         torch.cuda.synchronize()
         t_op = e0.elapsed_time(e1) / reps / 1e3
         abytes = 4.0 * (N * D + 2 * P * D + N * P)
-        # the GEMM kernel alone (operands staged once): the dominant kernel of the op
-        t_ka, kname = t_op, "mgp_logprob_fwd [N,P] (%s), whole op" % args.math
+        # `roofline` describes mgp_logprob_fwd AS CALLED by compute_log_prob (prototype operand pre-pass + the GEMM
+        # kernel; with isotropic sigma the x operand split is fused into the kernel: csrc/logprob_tcz.cu); the kernel
+        # alone (prototype operands pre-staged) is an extra key
         from mgproto_b200 import _lib
-        if args.math != "fp32" and _lib.load().mgp_has_tensor_core_path():
-            wss = [ops.logprob(xs[i], mu, sg, 0, math="tc", out=outs[0], return_ws=True)[1] for i in range(6)]
-            torch.cuda.synchronize()
-            e0.record()
-            for i in range(reps):
-                ops.logprob(xs[i % 6], mu, sg, 0, math="tc_reuse", ws=wss[i % 6], out=outs[i % 2])
-            e1.record()
-            torch.cuda.synchronize()
-            t_ka = e0.elapsed_time(e1) / reps / 1e3
-            kname = "logprob_tc_kernel [N,P] (tcgen05 fp16x3; operands pre-staged, 6 operand sets x 51 MB rotate)"
+        iso = ops.sigma_is_isotropic(sg)
+        kname = "mgp_logprob_fwd [N,P] as called (math=%s): %s" % (
+            args.math, "tc_proto_prep + logprob_z_kernel (TMEM-resident patch tile, fused fp16 hi/lo split, TMA-store epilogue)"
+            if (iso and args.math == "auto") else "operand pre-passes + logprob kernel")
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("logprob_dram_bytes_per_launch")
-        roof = {"kernel": kname, "bound": "hbm", "achieved": abytes / t_ka / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": abytes / t_ka / 1e9 / peak, "traffic": traffic,
-                "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst: kernel timed alone)",
-                "us_per_launch": t_ka * 1e6, "algorithmic_bytes": abytes,
-                "pairs_per_sec": N * P / t_ka, "tensor_tflops_equiv": 4.0 * N * P * D / t_ka / 1e12,
-                "note": "north-star kernel K-A (compute_log_prob / eval / push: log p materialised), timed alone; the "
-                        "labelled training step runs the max/arg-max variant instead (roofline_step_logprob) and its "
-                        "largest kernel is update_GMM (roofline_step_update_gmm)"}
-        extra["roofline_logprob_op"] = {"kernel": "mgp_logprob_fwd [N,P] (%s): operand prep (fp16 hi/lo split of x and "
-                                        "prototypes) + GEMM kernel" % args.math, "bound": "hbm",
-                                        "achieved": abytes / t_op / 1e9, "peak": peak, "unit": "GB/s",
-                                        "frac": abytes / t_op / 1e9 / peak, "us_per_launch": t_op * 1e6}
+        roof = {"kernel": kname, "bound": "hbm", "achieved": abytes / t_op / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": abytes / t_op / 1e9 / peak, "traffic": traffic,
+                "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst: op timed alone)",
+                "us_per_launch": t_op * 1e6, "algorithmic_bytes": abytes,
+                "pairs_per_sec": N * P / t_op, "tensor_tflops_equiv": 4.0 * N * P * D / t_op / 1e12,
+                "note": "north-star kernel K-A (compute_log_prob / eval / push: log p materialised), the whole op as the "
+                        "API calls it, 6 x 25.7 MB inputs and 2 x 401 MB outputs rotating; the [N,P] TMA-store stream "
+                        "alone tops out at 5.1-5.5 TB/s on this part (profiles/r2_tma_store_bw.txt); the labelled training "
+                        "step runs the max/arg-max variant instead (roofline_step_logprob)"}
+        if args.math != "fp32" and _lib.load().mgp_has_tensor_core_path():
+            mode_full, mode_reuse = ("tc_iso", "tc_iso_reuse") if iso and D in (64, 128, 256) else ("tc", "tc_reuse")
+            wss = [ops.logprob(xs[i], mu, sg, 0, math=mode_full, out=outs[0], return_ws=True)[1] for i in range(6)]
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(reps):
+                ops.logprob(xs[i % 6], mu, sg, 0, math=mode_reuse, ws=wss[i % 6], out=outs[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            t_ka = e0.elapsed_time(e1) / reps / 1e3
+            extra["roofline_logprob_kernel"] = {
+                "kernel": "the GEMM kernel alone (prototype operands pre-staged)", "bound": "hbm",
+                "achieved": abytes / t_ka / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / t_ka / 1e9 / peak,
+                "us_per_launch": t_ka * 1e6}
         del outs
         # the variant the labelled step runs: same GEMM, max/arg-max epilogue, no log p output -> tensor-bound
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops") if \
@@ -616,10 +622,11 @@ def main():
             t_ug = e0.elapsed_time(e1) / reps / 1e3
             ub = Lp * eb
             extra["roofline_step_update_gmm"] = {
-                "kernel": "update_GMM = em_plan + em_fused_kernel (200 active classes, %d EM loops; + one fill)" % Lp,
+                "kernel": "update_GMM = em_plan + em_tc_kernel (tcgen05; 200 active classes, %d EM loops; + one fill)" % Lp,
                 "bound": "hbm", "achieved": ub / t_ug / 1e9, "peak": peak, "unit": "GB/s", "frac": ub / t_ug / 1e9 / peak,
                 "us_per_call": t_ug * 1e6, "algorithmic_bytes": ub,
-                "note": "issue/barrier-bound (DESIGN.md 5.3): bank rows re-read per EM loop, L2-resident after the first"}
+                "note": "latency-bound chain per class (DESIGN.md 5.3): one CTA per class, 7 row tiles x 3 loops; the bank's "
+                        "fp16 hi/lo shadow (same bytes as the fp32 bank) is re-read per EM loop, L2-resident after the first"}
         except Exception as ex:  # noqa: BLE001 -- an auxiliary figure must never cost the bench line
             extra["roofline_step_update_gmm"] = {"error": str(ex)[:200]}
 

@@ -44,6 +44,7 @@ extern "C" {
                                prototype (true for every state the reference's loop reaches).
                                Extends the tensor-core path to D = 256; the kernel traps if the
                                assertion is false                                               */
+#define MGP_MATH_TC_ISO_REUSE 5 /* TC_ISO with the prototype-side operands already in ws (as TC_REUSE) */
 
 /* output layouts of mgp_logprob_fwd */
 #define MGP_OUT_LOGP_NP 0      /* out[n*P + p]           = log p      (ref: compute_log_prob)   */
@@ -148,6 +149,12 @@ int mgp_head_bwd(const float* grad_logits, const float* logits, const float* val
 int mgp_topt_pool(const float* sims_bphw, const float* x_nchw, float* vals, int32_t* idx, float* feats,
                   int B, int HW, int C, int K, int D, int T, void* stream);
 
+/* ---- f2  OoD / accuracy statistics of the test loop (ref train_and_test.py:184-199, :212-213) ---------------------
+ * out0: level-0 log evidences, element (b, c) at out0[b*stride_b + c*stride_c] (the [B,C,T] logits with stride_c = T,
+ * or a dense [B,C]).  p_sum[b] = sum_c exp(out0), p_mean[b] = p_sum / C, pred[b] = argmax_c (int64). */
+int mgp_ood_score(const float* out0, int stride_b, int stride_c, float* p_sum, float* p_mean,
+                  int64_t* pred, int B, int C, void* stream);
+
 /* ---- a8/a9  enqueue into the per-class FIFO bank -----------------------------------------
  * ref: model.py:225-250, utils/memory.py:31-73.
  *
@@ -162,12 +169,17 @@ int mgp_topt_pool(const float* sims_bphw, const float* x_nchw, float* vals, int3
  * cap keeps its first cap rows (the reference draws an unseeded random subset there).
  * updated[c] (uint8) is set for every class that received rows (ref model.py:250).
  * plan [B*K] int32 is scratch.  gt outside [0,C) skips the image. */
+/* rows_stride / top1_stride / gt_stride: elements (fp32 / int32 / int64) between consecutive IMAGES of rows / top1 / gt;
+ * 0 = dense (K*D / K / 1).  A batch-sharded run lets mgp_mined_gather write straight into packed per-image records
+ * [rows K*D | top1 K | gt] that one all-gather exchanges, and mgp_bank_enqueue read the gathered records in place. */
 int mgp_mined_gather(const float* xhat_nd, const int32_t* idx, const int64_t* gt, int32_t* top1,
-                     float* rows, int B, int HW, int C, int K, int D, int T, void* stream);
+                     float* rows, int rows_stride, int top1_stride, int B, int HW, int C, int K, int D,
+                     int T, void* stream);
 /* shadow_h / shadow_l [C,cap,D] fp16 and shadow_xx [C,cap] fp32 (all three or none): the tensor-core operand copy of
  * the bank -- hi / lo halves of 256 * row and |row|^2 -- kept in step by the scatter (see mgp_update_gmm). */
 int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, uint8_t* updated,
-                     const float* rows, const int32_t* top1, const int64_t* gt, int32_t* plan,
+                     const float* rows, const int32_t* top1, const int64_t* gt, int rows_stride,
+                     int top1_stride, int gt_stride, int32_t* plan,
                      void* shadow_h, void* shadow_l, float* shadow_xx,
                      int B, int C, int K, int D, int cap, void* stream);
 /* (Re)builds the whole shadow from the fp32 bank: after the bank was written by anything but mgp_bank_enqueue

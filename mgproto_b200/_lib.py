@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmgproto_b200.so")
 
-MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_AUTO, MGP_MATH_TC_REUSE, MGP_MATH_TC_ISO = 0, 1, 2, 3, 4
+MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_AUTO, MGP_MATH_TC_REUSE, MGP_MATH_TC_ISO, MGP_MATH_TC_ISO_REUSE = 0, 1, 2, 3, 4, 5
 MGP_OUT_LOGP_NP, MGP_OUT_LOGP_BPHW, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP = 0, 1, 2, 3
 
 _vp, _i, _f, _sz, _d = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_double
@@ -32,8 +32,8 @@ SIGNATURES = {
     "mgp_head_select_top1": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
     "mgp_head_bwd_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "mgp_head_bwd": (_i, [_vp] * 11 + [_sz, _vp] + [_i] * 6 + [_vp]),
-    "mgp_mined_gather": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
-    "mgp_bank_enqueue": (_i, [_vp] * 11 + [_i] * 5 + [_vp]),
+    "mgp_mined_gather": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "mgp_bank_enqueue": (_i, [_vp] * 7 + [_i] * 3 + [_vp] * 4 + [_i] * 5 + [_vp]),
     "mgp_bank_shadow_sync": (_i, [_vp] * 4 + [_i] * 3 + [_vp]),
     "mgp_bank_linearize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_stat_stride": (_sz, [_i, _i, _i]),
@@ -46,6 +46,7 @@ SIGNATURES = {
     "mgp_em_estep": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_mstep_closed": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_mstep_div": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mgp_ood_score": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "mgp_topt_pool": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "mgp_mine_ce": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mgp_push_argmin": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -80,7 +80,7 @@ extern "C" int mgp_has_tensor_core_path(void) {
 extern "C" size_t mgp_logprob_ws_bytes(int B, int HW, int P, int D, int math) {
     size_t simt = ((size_t)P * D + P) * sizeof(float);
 #ifdef MGP_WITH_TC
-    if (math != MGP_MATH_FP32 && mgp_logprob_tc_supported(0, B, HW, P, D, math == MGP_MATH_TC_ISO)) {
+    if (math != MGP_MATH_FP32 && mgp_logprob_tc_supported(0, B, HW, P, D, math == MGP_MATH_TC_ISO || math == MGP_MATH_TC_ISO_REUSE)) {
         size_t tc = mgp_logprob_tc_ws_bytes((long long)B * HW, P, D);
         return tc > simt ? tc : simt;
     }
@@ -102,14 +102,16 @@ extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const floa
     if (ws_bytes < mgp_logprob_ws_bytes(B, HW, P, D, math)) return MGP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
 #ifdef MGP_WITH_TC
-    if (math == MGP_MATH_TC || math == MGP_MATH_AUTO || math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO) {
-        if (mgp_logprob_tc_supported(out_layout, B, HW, P, D, math == MGP_MATH_TC_ISO))
+    const bool iso_mode = (math == MGP_MATH_TC_ISO || math == MGP_MATH_TC_ISO_REUSE);
+    if (math == MGP_MATH_TC || math == MGP_MATH_AUTO || math == MGP_MATH_TC_REUSE || iso_mode) {
+        if (mgp_logprob_tc_supported(out_layout, B, HW, P, D, iso_mode))
             return mgp_logprob_tc_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D, ws, ws_bytes,
-                                         math == MGP_MATH_TC_REUSE, math == MGP_MATH_TC_ISO, st);
+                                         math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO_REUSE, iso_mode, st);
         if (math != MGP_MATH_AUTO) return MGP_ERR_UNSUPPORTED;
     }
 #else
-    if (math == MGP_MATH_TC || math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO) return MGP_ERR_UNSUPPORTED;
+    if (math == MGP_MATH_TC || math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO || math == MGP_MATH_TC_ISO_REUSE)
+        return MGP_ERR_UNSUPPORTED;
 #endif
     if (out_layout == MGP_OUT_TOP1_BP) return MGP_ERR_UNSUPPORTED;   // fused max/arg-max exists on the tensor-core path only
     return mgp_logprob_simt_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D,

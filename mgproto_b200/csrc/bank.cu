@@ -48,7 +48,9 @@ __global__ void bank_shadow_kernel(const float* __restrict__ bank, __half* __res
 __global__ void __launch_bounds__(1024)
 enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, uint8_t* __restrict__ updated,
                     const int32_t* __restrict__ top1_bk, const int64_t* __restrict__ gt, int32_t* __restrict__ plan,
-                    int B, int C, int K, int cap) {
+                    int B, int C, int K, int cap, int top1_stride, int gt_stride) {
+    // top1_stride / gt_stride: elements between consecutive images (K / 1 when dense; the record stride when the
+    // inputs are views into the all-gathered packed records of a batch-sharded run, parallel.py)
     extern __shared__ int sm[];
     int* ucount = sm;       // [B] unique rows of image b
     int* cls = sm + B;      // [B] class or -1
@@ -57,9 +59,9 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
     if (K <= 32) {
         // warp per image, lane per prototype: duplicates by MATCH.ANY, rank among the distinct values by K shuffles
         for (int b = warp; b < B; b += nwarp) {
-            const long long c = gt[b];
+            const long long c = gt[(size_t)b * gt_stride];
             const bool okc = (c >= 0 && c < C);
-            const int v = (okc && lane < K) ? top1_bk[(size_t)b * K + lane] : (-1 - lane);
+            const int v = (okc && lane < K) ? top1_bk[(size_t)b * top1_stride + lane] : (-1 - lane);
             const unsigned m = __match_any_sync(0xffffffffu, v);
             const bool first = okc && lane < K && (__ffs(m) - 1 == lane);
             const unsigned fm = __ballot_sync(0xffffffffu, first);
@@ -73,7 +75,7 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
         }
     } else {
         for (int b = threadIdx.x; b < B; b += blockDim.x) {
-            const long long c = gt[b];
+            const long long c = gt[(size_t)b * gt_stride];
             if (c < 0 || c >= C) {
                 cls[b] = -1;
                 ucount[b] = 0;
@@ -81,7 +83,7 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
                 continue;
             }
             cls[b] = (int)c;
-            const int32_t* top1 = top1_bk + (size_t)b * K;
+            const int32_t* top1 = top1_bk + (size_t)b * top1_stride;
             int u = 0;
             for (int k = 0; k < K; ++k) {
                 const int v = top1[k];
@@ -194,20 +196,21 @@ enqueue_plan_kernel(int64_t* __restrict__ mem_len, int32_t* __restrict__ head, u
 // top-1 patch of each of the GT class's K prototypes: spatial index and feature row
 __global__ void mined_gather_kernel(const float* __restrict__ xhat, const int32_t* __restrict__ idx,
                                     const int64_t* __restrict__ gt, int32_t* __restrict__ top1,
-                                    float* __restrict__ rows, int B, int HW, int C, int K, int D, int T) {
+                                    float* __restrict__ rows, int B, int HW, int C, int K, int D, int T, int rows_stride,
+                                    int top1_stride) {
     const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (wg >= B * K) return;
     const int b = wg / K, k = wg - b * K;
     const long long c = gt[b];
-    float4* dst = reinterpret_cast<float4*>(rows + (size_t)wg * D);
+    float4* dst = reinterpret_cast<float4*>(rows + (size_t)b * rows_stride + (size_t)k * D);
     if (c < 0 || c >= C) {
-        if (lane == 0) top1[wg] = -1;
+        if (lane == 0) top1[(size_t)b * top1_stride + k] = -1;
         for (int d = lane; d < D / 4; d += 32) dst[d] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
     const int n = idx[((size_t)b * C * K + (size_t)c * K + k) * T];     // level 0 (ref model.py:225-226)
-    if (lane == 0) top1[wg] = n;
+    if (lane == 0) top1[(size_t)b * top1_stride + k] = n;
     const float4* src = reinterpret_cast<const float4*>(xhat + ((size_t)b * HW + n) * D);
     for (int d = lane; d < D / 4; d += 32) dst[d] = src[d];
 }
@@ -215,17 +218,19 @@ __global__ void mined_gather_kernel(const float* __restrict__ xhat, const int32_
 __global__ void enqueue_scatter_kernel(float* __restrict__ bank, const float* __restrict__ rows,
                                        const int64_t* __restrict__ gt, const int32_t* __restrict__ plan,
                                        __half* __restrict__ xh, __half* __restrict__ xl, float* __restrict__ xx, int B,
-                                       int K, int D, int cap) {
+                                       int K, int D, int cap, int rows_stride, int gt_stride) {
     const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (wg >= B * K) return;
     const int slot = plan[wg];
     if (slot < 0) return;
-    const long long c = gt[wg / K];
-    const float4* src = reinterpret_cast<const float4*>(rows + (size_t)wg * D);
+    const int sb = wg / K, sk = wg - sb * K;
+    const long long c = gt[(size_t)sb * gt_stride];
+    const float* srow = rows + (size_t)sb * rows_stride + (size_t)sk * D;
+    const float4* src = reinterpret_cast<const float4*>(srow);
     float4* dst = reinterpret_cast<float4*>(bank + ((size_t)c * cap + slot) * D);
     for (int d = lane; d < D / 4; d += 32) dst[d] = src[d];
-    if (xh) shadow_store_row(rows + (size_t)wg * D, xh, xl, xx, (size_t)c * cap + slot, D, lane);   // keep the shadow in step
+    if (xh) shadow_store_row(srow, xh, xl, xx, (size_t)c * cap + slot, D, lane);   // keep the shadow in step
 }
 
 __global__ void bank_linearize_kernel(const float* __restrict__ bank, const int64_t* __restrict__ mem_len,
@@ -247,30 +252,41 @@ __global__ void bank_linearize_kernel(const float* __restrict__ bank, const int6
 }  // namespace
 
 extern "C" int mgp_mined_gather(const float* xhat_nd, const int32_t* idx, const int64_t* gt, int32_t* top1,
-                               float* rows, int B, int HW, int C, int K, int D, int T, void* stream) {
+                               float* rows, int rows_stride, int top1_stride, int B, int HW, int C, int K, int D, int T,
+                               void* stream) {
     if (!xhat_nd || !idx || !gt || !top1 || !rows) return MGP_ERR_INVALID;
     if (B <= 0 || HW <= 0 || C <= 0 || K <= 0 || D <= 0 || T <= 0 || (D & 3)) return MGP_ERR_INVALID;
+    if (rows_stride == 0) rows_stride = K * D;
+    if (top1_stride == 0) top1_stride = K;
+    if (rows_stride < K * D || (rows_stride & 3) || top1_stride < K || !mgp_aligned16(rows)) return MGP_ERR_INVALID;
     const int warps = B * K;
-    mined_gather_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(xhat_nd, idx, gt, top1, rows, B, HW, C, K, D, T);
+    mined_gather_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(xhat_nd, idx, gt, top1, rows, B, HW, C, K, D, T,
+                                                                          rows_stride, top1_stride);
     MGP_CHECK_LAUNCH();
     return MGP_OK;
 }
 
 extern "C" int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, uint8_t* updated, const float* rows,
-                                const int32_t* top1, const int64_t* gt, int32_t* plan, void* shadow_h, void* shadow_l,
-                                float* shadow_xx, int B, int C, int K, int D, int cap, void* stream) {
+                                const int32_t* top1, const int64_t* gt, int rows_stride, int top1_stride, int gt_stride,
+                                int32_t* plan, void* shadow_h, void* shadow_l, float* shadow_xx, int B, int C, int K, int D,
+                                int cap, void* stream) {
     if (!bank || !mem_len || !head || !updated || !rows || !top1 || !gt || !plan) return MGP_ERR_INVALID;
     if ((shadow_h != nullptr) != (shadow_l != nullptr) || (shadow_h != nullptr) != (shadow_xx != nullptr)) return MGP_ERR_INVALID;
     if (B <= 0 || C <= 0 || K <= 0 || D <= 0 || cap <= 0 || (D & 3)) return MGP_ERR_INVALID;
     if (B > 8192 || K > 64) return MGP_ERR_UNSUPPORTED;
+    if (rows_stride == 0) rows_stride = K * D;
+    if (top1_stride == 0) top1_stride = K;
+    if (gt_stride == 0) gt_stride = 1;
+    if (rows_stride < K * D || (rows_stride & 3) || top1_stride < K || gt_stride < 1 || !mgp_aligned16(rows)) return MGP_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     size_t smem = (size_t)4 * B * sizeof(int);
     MGP_CUDA(cudaFuncSetAttribute(enqueue_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    enqueue_plan_kernel<<<1, 1024, smem, st>>>(mem_len, head, updated, top1, gt, plan, B, C, K, cap);
+    enqueue_plan_kernel<<<1, 1024, smem, st>>>(mem_len, head, updated, top1, gt, plan, B, C, K, cap, top1_stride, gt_stride);
     MGP_CHECK_LAUNCH();
     const int warps = B * K;
     enqueue_scatter_kernel<<<(warps + 7) / 8, 256, 0, st>>>(bank, rows, gt, plan, reinterpret_cast<__half*>(shadow_h),
-                                                            reinterpret_cast<__half*>(shadow_l), shadow_xx, B, K, D, cap);
+                                                            reinterpret_cast<__half*>(shadow_l), shadow_xx, B, K, D, cap,
+                                                            rows_stride, gt_stride);
     MGP_CHECK_LAUNCH();
     return MGP_OK;
 }

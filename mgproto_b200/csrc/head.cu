@@ -876,6 +876,44 @@ __global__ void topt_gather_kernel(const float* __restrict__ x, const int32_t* _
 }
 }  // namespace
 
+// f2 (ref train_and_test.py:184-199, :212-213): per image, from the level-0 log evidences out0 [B,C]:
+//   p_sum = sum_c exp(out0), p_mean = p_sum / C (the reference thresholds on the sum and tests the mean), pred = argmax_c.
+namespace {
+__global__ void ood_score_kernel(const float* __restrict__ out0, int stride_b, int stride_c, float* __restrict__ p_sum,
+                                 float* __restrict__ p_mean, int64_t* __restrict__ pred, int B, int C) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float s = 0.f, best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+        const float v = out0[(size_t)b * stride_b + (size_t)c * stride_c];
+        s += expf(v);
+        if (v > best) { best = v; bi = c; }
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                      // max value, smallest index among equals (torch.argmax on CUDA)
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) {
+        p_sum[b] = s;
+        p_mean[b] = s / (float)C;
+        pred[b] = bi;
+    }
+}
+}  // namespace
+
+extern "C" int mgp_ood_score(const float* out0, int stride_b, int stride_c, float* p_sum, float* p_mean, int64_t* pred,
+                             int B, int C, void* stream) {
+    if (!out0 || !p_sum || !p_mean || !pred || B <= 0 || C <= 0 || stride_b <= 0 || stride_c <= 0) return MGP_ERR_INVALID;
+    ood_score_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(out0, stride_b, stride_c, p_sum, p_mean, pred, B, C);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}
+
 extern "C" int mgp_topt_pool(const float* sims_bphw, const float* x_nchw, float* vals, int32_t* idx, float* feats, int B,
                              int HW, int C, int K, int D, int T, void* stream) {
     if (!sims_bphw || !vals || !idx || (feats && !x_nchw) || D <= 0) return MGP_ERR_INVALID;

@@ -149,33 +149,39 @@ class MGProto(nn.Module):
             with torch.no_grad():
                 q = self.queue
                 gt = gt.contiguous()
-                top1, rows = ops.mined_gather(xhat, idx, gt, x_add.shape[2] * x_add.shape[3], self.num_classes,
-                                              self.num_prototypes_per_class)
-                if self.em_group is not None and self.overlap_enqueue:
-                    # batch-sharded replicas: the exchange of the mined rows and the enqueue run on a side stream and
-                    # overlap this step's loss / backward (nothing there reads the bank); update_GMM waits for them.
-                    # The inputs stay referenced until the main stream has waited (no record_stream: that would park
-                    # their blocks in the allocator's deferred-free list and force fresh cudaMallocs every step).
-                    from .parallel import all_gather_mined
-                    self.wait_enqueue()
-                    cur = torch.cuda.current_stream()
-                    if self._side_stream is None:
-                        self._side_stream = torch.cuda.Stream(device=x_add.device)
-                    side = self._side_stream
-                    side.wait_stream(cur)
-                    with torch.cuda.stream(side):
-                        t1, r1, g1 = all_gather_mined(top1, rows, gt, self.em_group)
+                HWn, Kn = x_add.shape[2] * x_add.shape[3], self.num_prototypes_per_class
+                if self.em_group is not None:
+                    # batch-sharded replicas: the gather kernel writes packed per-image records, ONE all-gather exchanges
+                    # them, the enqueue kernels read the gathered buffer in place (no packing / unpacking copies)
+                    from .parallel import all_gather_records
+                    rec, _, _ = ops.mined_gather(xhat, idx, gt, HWn, self.num_classes, Kn, packed=True)
+                    Dn = xhat.shape[1]
+                    if self.overlap_enqueue:
+                        # exchange + enqueue on a side stream, overlapping this step's loss / backward (nothing there
+                        # reads the bank).  The inputs stay referenced until a later access waits (no record_stream:
+                        # that would park their blocks in the allocator's deferred-free list).
+                        self.wait_enqueue()
+                        cur = torch.cuda.current_stream()
+                        if self._side_stream is None:
+                            self._side_stream = torch.cuda.Stream(device=x_add.device)
+                        side = self._side_stream
+                        side.wait_stream(cur)
+                        with torch.cuda.stream(side):
+                            buf = all_gather_records(rec, self.em_group)
+                            r1, t1, g1 = ops._rec_views(buf, Kn, Dn)
+                            ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, r1, t1, g1, shadow=q.shadow_if_valid())
+                            done = torch.cuda.Event()
+                            done.record(side)
+                            del buf, r1, t1, g1                                   # side-stream blocks: reused in stream order
+                        # the bank remembers the event: every later access to its tensors (mem_len in the training loop,
+                        # state_dict, push, update_GMM) first makes its stream wait for this enqueue
+                        q.set_pending(done, (rec,))
+                    else:
+                        buf = all_gather_records(rec, self.em_group)
+                        r1, t1, g1 = ops._rec_views(buf, Kn, Dn)
                         ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, r1, t1, g1, shadow=q.shadow_if_valid())
-                        done = torch.cuda.Event()
-                        done.record(side)
-                        del t1, r1, g1                                            # side-stream blocks: reused in stream order
-                    # the bank remembers the event: every later access to its tensors (mem_len in the training loop,
-                    # state_dict, push, update_GMM) first makes its stream wait for this enqueue
-                    q.set_pending(done, (top1, rows, gt))
                 else:
-                    if self.em_group is not None:                                 # batch-sharded replicas
-                        from .parallel import all_gather_mined
-                        top1, rows, gt = all_gather_mined(top1, rows, gt, self.em_group)
+                    top1, rows = ops.mined_gather(xhat, idx, gt, HWn, self.num_classes, Kn)
                     ops.bank_enqueue(q.bank, q.mem_len, q.head, q.updated, rows, top1, gt, shadow=q.shadow_if_valid())
                 self.iteration_counter += 1                                       # ref :252
         return logits

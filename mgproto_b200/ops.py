@@ -11,15 +11,16 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, MGP_MATH_TC_REUSE, MGP_OUT_LOGP_BPHW,
+from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, MGP_MATH_TC_ISO_REUSE, MGP_MATH_TC_REUSE,
+                   MGP_OUT_LOGP_BPHW,
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP, check)
 
 __all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_level0", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
-           "bank_linearize", "bank_shadow_sync", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "em_mstep_div", "topt_pool", "push_argmin", "mine_cross_entropy",
+           "bank_linearize", "bank_shadow_sync", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "em_mstep_div", "topt_pool", "ood_score", "push_argmin", "mine_cross_entropy",
            "MATH_MODES"]
 
 MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE,
-              "tc_iso": MGP_MATH_TC_ISO}
+              "tc_iso": MGP_MATH_TC_ISO, "tc_iso_reuse": MGP_MATH_TC_ISO_REUSE}
 
 _iso_cache = {}
 
@@ -171,7 +172,7 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
         raise RuntimeError("mgproto_b200: workspace too small")
     check(lib.mgp_logprob_fwd(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), float(eps), float(eps_log), out.data_ptr(),
                               int(layout), B_, HW_, P, D, m, ws.data_ptr(), nbytes, _stream()), "mgp_logprob_fwd")
-    _count(1 if m == MGP_MATH_TC_REUSE else (3 if nbytes > (P * D + P) * 4 else 2))
+    _count(1 if m in (MGP_MATH_TC_REUSE, MGP_MATH_TC_ISO_REUSE) else (3 if nbytes > (P * D + P) * 4 else 2))
     return (out, ws) if return_ws else out
 
 
@@ -346,18 +347,45 @@ def head_forward(x_add, mu_ckd, sigma_ckd, weight_cp, gt, T, math="auto"):
 
 
 # ----------------------------------------------------------------------------------- a8/a9
+def _rec_stride(K, D):
+    """fp32 words of one packed per-image record [rows K*D | top1 K (int32 bits) | gt (int64 bits) | pad]: a multiple
+    of 4 (16-byte row alignment for the vector loads) with the int64 on an 8-byte boundary."""
+    return ((K * D + K + 1) // 2 * 2 + 2 + 3) // 4 * 4
+
+
+def _rec_views(rec, K, D):
+    """(rows [b, K*D] fp32, top1 [b, K] int32, gt [b] int64) views into packed records [b, stride]."""
+    off = (K * D + K + 1) // 2 * 2
+    rows = rec[:, :K * D]
+    top1 = rec.view(torch.int32)[:, K * D:K * D + K]
+    gt = rec.view(torch.int64)[:, off // 2]
+    return rows, top1, gt
+
+
 @_on_device
-def mined_gather(xhat_nd, idx, gt, HW, C, K):
-    """ref model.py:225-226: (top1 [B,K] int32, rows [B,K,D]) of every image's GT-class prototypes."""
+def mined_gather(xhat_nd, idx, gt, HW, C, K, packed=False):
+    """ref model.py:225-226: (top1 [B,K] int32, rows [B,K,D]) of every image's GT-class prototypes.  packed=True: the
+    kernel writes them straight into per-image records [B, _rec_stride(K, D)] (+ the label), the unit a batch-sharded run
+    all-gathers (parallel.py); returns (records, top1 view, rows view)."""
     _req(xhat_nd, torch.float32, "xhat")
     _req(idx, torch.int32, "idx")
     _req(gt, torch.int64, "gt")
     B, P, T = idx.shape
     D = xhat_nd.shape[1]
+    lib = _lib.load()
+    if packed:
+        rs = _rec_stride(K, D)
+        rec = torch.empty((B, rs), device=idx.device, dtype=torch.float32)
+        rows, top1, gtv = _rec_views(rec, K, D)
+        gtv.copy_(gt)
+        check(lib.mgp_mined_gather(xhat_nd.data_ptr(), idx.data_ptr(), gt.data_ptr(), top1.data_ptr(), rows.data_ptr(), rs, rs,
+                                   B, HW, C, K, D, T, _stream()), "mgp_mined_gather")
+        _count(1)
+        return rec, top1, rows
     top1 = torch.empty((B, K), device=idx.device, dtype=torch.int32)
     rows = torch.empty((B, K, D), device=idx.device, dtype=torch.float32)
-    check(_lib.load().mgp_mined_gather(xhat_nd.data_ptr(), idx.data_ptr(), gt.data_ptr(), top1.data_ptr(),
-                                       rows.data_ptr(), B, HW, C, K, D, T, _stream()), "mgp_mined_gather")
+    check(lib.mgp_mined_gather(xhat_nd.data_ptr(), idx.data_ptr(), gt.data_ptr(), top1.data_ptr(), rows.data_ptr(), 0, 0,
+                               B, HW, C, K, D, T, _stream()), "mgp_mined_gather")
     _count(1)
     return top1, rows
 
@@ -365,23 +393,28 @@ def mined_gather(xhat_nd, idx, gt, HW, C, K):
 @_on_device
 def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt, shadow=None):
     """ref model.py:228-250 + utils/memory.py:31-73, in place on (bank, mem_len, head, updated); ``shadow`` =
-    (shadow_h, shadow_l, shadow_xx) keeps the tensor-core operand copy of the bank in step (MemoryBank.ensure_shadow)."""
+    (shadow_h, shadow_l, shadow_xx) keeps the tensor-core operand copy of the bank in step (MemoryBank.ensure_shadow).
+    rows / top1 / gt may be the strided views of packed records (`_rec_views`): they are read in place."""
     bank = _req(bank, torch.float32, "bank")
     C, cap, D = bank.shape
     B, K = top1.shape
     _req(mem_len, torch.int64, "mem_len")
     _req(head, torch.int32, "head")
     _req(updated, torch.uint8, "updated")
-    _req(rows, torch.float32, "rows")
-    _req(top1, torch.int32, "top1")
-    _req(gt, torch.int64, "gt")
-    if rows.shape != (B, K, D) or gt.shape != (B,):
+    for t, dt, nm in ((rows, torch.float32, "rows"), (top1, torch.int32, "top1"), (gt, torch.int64, "gt")):
+        if not t.is_cuda or t.dtype != dt:
+            raise RuntimeError("mgproto_b200: %s must be a CUDA %s tensor" % (nm, dt))
+    if rows.numel() != B * K * D or gt.shape != (B,) or rows.stride(-1) != 1 or top1.stride(-1) != 1:
         raise RuntimeError("mgproto_b200: enqueue shape mismatch")
+    rs = rows.stride(0) if B > 1 else 0
+    ts = top1.stride(0) if B > 1 else 0
+    gs = gt.stride(0) if B > 1 else 0
     plan = torch.empty((B * K,), device=bank.device, dtype=torch.int32)
     sh = shadow if shadow is not None else (None, None, None)
     check(_lib.load().mgp_bank_enqueue(bank.data_ptr(), mem_len.data_ptr(), head.data_ptr(), updated.data_ptr(),
-                                       rows.data_ptr(), top1.data_ptr(), gt.data_ptr(), plan.data_ptr(), _p(sh[0]),
-                                       _p(sh[1]), _p(sh[2]), B, C, K, D, cap, _stream()), "mgp_bank_enqueue")
+                                       rows.data_ptr(), top1.data_ptr(), gt.data_ptr(), int(rs), int(ts), int(gs),
+                                       plan.data_ptr(), _p(sh[0]), _p(sh[1]), _p(sh[2]), B, C, K, D, cap, _stream()),
+          "mgp_bank_enqueue")
     _count(2)
 
 
@@ -543,6 +576,22 @@ def topt_pool(sims_bphw, x_nchw, T, C, K, want_feats=True):
                                     _stream()), "mgp_topt_pool")
     _count(2 if want_feats else 1)
     return vals, idx, feats
+
+
+@_on_device
+def ood_score(out0):
+    """ref train_and_test.py:184-199, :212-213 on level-0 log evidences [B,C] (any strides): -> (p_sum [B], p_mean [B],
+    pred [B] int64)."""
+    if not out0.is_cuda or out0.dtype != torch.float32 or out0.dim() != 2:
+        raise RuntimeError("mgproto_b200: out0 must be a CUDA fp32 [B, C] tensor")
+    B, C = out0.shape
+    ps = torch.empty((B,), device=out0.device, dtype=torch.float32)
+    pm = torch.empty((B,), device=out0.device, dtype=torch.float32)
+    pred = torch.empty((B,), device=out0.device, dtype=torch.int64)
+    check(_lib.load().mgp_ood_score(out0.data_ptr(), out0.stride(0), out0.stride(1), ps.data_ptr(), pm.data_ptr(),
+                                    pred.data_ptr(), B, C, _stream()), "mgp_ood_score")
+    _count(1)
+    return ps, pm, pred
 
 
 # ----------------------------------------------------------------------------------- a17 (optional)

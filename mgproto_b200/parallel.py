@@ -5,9 +5,10 @@ The path shards by image: the head (log-likelihood, top-T, logits, backward) tou
 image's patches against replicated prototypes -- no communication.  Two exchanges keep every
 rank's memory bank and prototypes identical to a single-GPU run on the concatenated batch:
 
-* ``all_gather_mined``: the per-image mined rows (top1 [B,K], rows [B,K,D], gt [B]; ~1.3 MB at
-  B=256, K=10, D=128) are all-gathered in rank (= global image) order before the enqueue, so
-  every replica of the bank receives the whole global batch in the reference's order;
+* ``all_gather_records``: the per-image mined rows (top1 [B,K], rows [B,K,D], gt [B]; ~1.3 MB at
+  B=256, K=10, D=128), packed into one fp32 record per image BY the gather kernel, are all-gathered in rank
+  (= global image) order before the enqueue and read in place by the enqueue kernels, so every replica of the bank
+  receives the whole global batch in the reference's order;
 * ``update_GMM`` needs no exchange: the bank is replicated, the EM kernels are deterministic, so every rank runs
   the whole (single-launch) update on its replica and all replicas stay bit-identical.  With
   ``model.em_shard = True`` the rows are sharded instead (``shard_rows``) and the packed statistics
@@ -33,23 +34,38 @@ def shard_batch(global_batch: int, world: int, rank: int):
     return rank * per, (rank + 1) * per
 
 
+def all_gather_records(rec, group=None):
+    """All-gather the packed per-image records ``ops.mined_gather(..., packed=True)`` wrote ([b, stride] fp32: rows,
+    top-1 indices and label of every local image) in rank (= global image) order: ONE collective, no packing or
+    unpacking copies -- the gather kernel writes the send buffer and the enqueue kernels read the receive buffer in
+    place through strided views (ops._rec_views).  Every rank must contribute the same number of images (the
+    reference's loaders use a fixed batch size; use drop_last=True): the collective's buffers are sized from it."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return rec
+    buf = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(buf, rec, group=group)
+    return buf
+
+
 def all_gather_mined(top1, rows, gt, group=None):
-    """Concatenate every rank's (top1 [b,K] int32, rows [b,K,D] fp32, gt [b] int64) in rank order.
-    One collective: the three tensors travel as one [b, K*D + K + 2] fp32 record per image (bit-casts)."""
+    """(top1 [b,K] int32, rows [b,K,D] fp32, gt [b] int64) of every rank concatenated in rank order -- the tensor-level
+    form of the exchange (the model's step uses ``all_gather_records``, which skips the packing below)."""
+    from . import ops
     world = dist.get_world_size(group)
     if world == 1:
         return top1, rows, gt
     b, K, D = rows.shape
     if top1.dtype != torch.int32 or gt.dtype != torch.int64 or rows.dtype != torch.float32:
         raise TypeError("all_gather_mined expects int32 top1, fp32 rows, int64 gt")
-    rec = torch.cat([rows.reshape(b, K * D), top1.contiguous().view(torch.float32),
-                     gt.contiguous().view(torch.float32).reshape(b, 2)], dim=1)
-    buf = torch.empty((world * b, K * D + K + 2), dtype=torch.float32, device=rows.device)
-    dist.all_gather_into_tensor(buf, rec, group=group)
-    rows_all = buf[:, :K * D].reshape(world * b, K, D).contiguous()
-    top1_all = buf[:, K * D:K * D + K].contiguous().view(torch.int32)
-    gt_all = buf[:, K * D + K:].contiguous().view(torch.int64).reshape(world * b)
-    return top1_all, rows_all, gt_all
+    rec = torch.empty((b, ops._rec_stride(K, D)), dtype=torch.float32, device=rows.device)
+    r, t, g = ops._rec_views(rec, K, D)
+    r.copy_(rows.reshape(b, K * D))
+    t.copy_(top1)
+    g.copy_(gt)
+    buf = all_gather_records(rec, group)
+    r, t, g = ops._rec_views(buf, K, D)
+    return t.contiguous(), r.reshape(world * b, K, D).contiguous(), g.contiguous()
 
 
 def attach(model, group=None):

@@ -148,6 +148,6 @@ def test_header_constants_match_binding():
     hdr = open(os.path.join(ROOT, "include", "mgproto_b200.h")).read()
     defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(MGP_[A-Z0-9_]+)\s+(-?\d+)\b", hdr)}
     for name in ("MGP_OUT_LOGP_NP", "MGP_OUT_LOGP_BPHW", "MGP_OUT_NEGP_BPHW", "MGP_OUT_TOP1_BP", "MGP_MATH_FP32",
-                 "MGP_MATH_TC", "MGP_MATH_AUTO", "MGP_MATH_TC_REUSE", "MGP_MATH_TC_ISO"):
+                 "MGP_MATH_TC", "MGP_MATH_AUTO", "MGP_MATH_TC_REUSE", "MGP_MATH_TC_ISO", "MGP_MATH_TC_ISO_REUSE"):
         assert name in defs, name
         assert getattr(_lib, name) == defs[name], name

@@ -617,3 +617,145 @@ def test_head_level0_matches_unlabelled_head(golden, math):
         l0 = net.head_level0(x)
     np.testing.assert_allclose(l0.cpu().numpy(), full[:, :, 0].cpu().numpy(), rtol=RTOL, atol=1e-6)
     np.testing.assert_allclose(l0.cpu().numpy(), g["it0_logits_nogt"][:, :, 0], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_reference_training_body_with_real_backbone():
+    """construct_MGProto('resnet18') driven by the body of the reference's training loop (train_and_test.py:26-63):
+    forward(image, target) through a real backbone, the CE + mining losses, backward into the backbone, the joint
+    optimiser step, then update_GMM once the banks are full -- two iterations.  The logits are checked against the
+    float64 oracle on the add-on features the backbone produced, the enqueue against the oracle's, and the gradient
+    must reach the backbone."""
+    import mgproto_b200 as M
+    from oracle import mgproto_oracle as O
+    torch.manual_seed(0)
+    C, K, D, T, cap, B = 6, 4, 64, 4, 8, 12
+    net = M.construct_MGProto("resnet18", pretrained=False, img_size=64, prototype_shape=(C * K, D, 1, 1), num_classes=C,
+                              add_on_layers_type="regular", sz_embedding=16, mem_capacity=cap, mine_K=T).to(_dev())
+    assert net.proto_layer_rf_info is not None and len(net.proto_layer_rf_info) == 4
+    net.prototype_optimizer = torch.optim.Adam([{"params": net.prototype_means, "lr": 3e-3}])
+    joint = torch.optim.Adam([{"params": net.features.parameters(), "lr": 1e-4},
+                              {"params": net.add_on_layers.parameters(), "lr": 3e-3}])
+    model = torch.nn.DataParallel(net, device_ids=[0])                      # the reference drives `.module` (train_and_test.py:61)
+    net.train()
+    g = torch.Generator().manual_seed(1)
+    bank = O.MemoryBankOracle(C, D, cap)
+    for it in range(2):
+        image = torch.randn(B, 3, 64, 64, generator=g).to(_dev())
+        target = torch.randint(0, C, (B,), generator=g).to(_dev())
+        output, x_aux = model(image, target)
+        assert output.shape == (B, C, T) and x_aux.shape == (B, 16)
+        mine_loss = sum(F.cross_entropy(output[:, :, k], target) for k in range(1, T)) / (T - 1)
+        loss = F.cross_entropy(output[:, :, 0], target) + 0.2 * mine_loss
+        joint.zero_grad()
+        loss.backward()
+        gn = sum(float(p.grad.abs().sum()) for p in net.features.parameters() if p.grad is not None)
+        assert np.isfinite(gn) and gn > 0
+        # oracle on the features the (unchanged-so-far) backbone produced
+        with torch.no_grad():
+            x_add, _ = net.conv_features(image)
+        fw = O.head_forward(x_add.double().cpu().numpy(), net.prototype_means.detach().double().cpu().numpy(),
+                            net.prototype_covs.double().cpu().numpy(), net.last_layer.weight.double().cpu().numpy(),
+                            target.cpu().numpy(), T)
+        np.testing.assert_allclose(output.detach().cpu().numpy(), fw["logits"], rtol=RTOL, atol=1e-5)
+        for c, rows in O.enqueue_rows(fw["xhat"].astype(np.float32), fw["idx"], target.cpu().numpy(), C, K, x_add.shape[2] * x_add.shape[3]):
+            bank.push(c, rows)
+        np.testing.assert_array_equal(net.queue.mem_len.cpu().numpy(), bank.mem_len)
+        joint.step()
+        # train_and_test.py:61-63
+        if model.module.queue.mem_len.sum() > 0 and model.module.iteration_counter % model.module.update_interval == 0:
+            mu0 = net.prototype_means.detach().clone()
+            model.module.update_GMM()
+            full = (net.queue.mem_len == cap).cpu().numpy()
+            moved = (net.prototype_means.detach() - mu0).abs().amax(dim=(1, 2)).cpu().numpy() > 0
+            assert (moved[full] | ~full[full]).all() or not full.any()
+        assert int(net.memory_updated_cls.sum()) == 0
+    net.sync_optimizer_state()
+    assert torch.isfinite(net.prototype_means).all() and torch.isfinite(net.last_layer.weight).all()
+
+
+@pytest.mark.gpu
+def test_boundary_methods_m_step_diversified_and_topT(golden):
+    """The reference's private methods as a caller would drive them: _e_step -> _m_step_diversified on a bank class
+    (gradient = the reference's autograd gradient, then the optimiser step on the whole mean tensor) and
+    global_max_pooling_gmm_topT on probabilities (values / indices / gathered features)."""
+    g = golden
+    if "em_div_grad" not in g or g["em_x"].shape[0] < 2:
+        pytest.skip("fixture without a full EM class")
+    net = _model_from(g, "fp32")
+    C, K, D = (int(g[k]) for k in "C K D".split())
+    c = int(g["em_class"])
+    net.prototype_means.data[c].copy_(_t(g["em_mu"][0]))
+    net.prototype_covs.data[c].copy_(_t(g["em_sigma"][0]))
+    x = _t(g["em_x"])
+    pi_old = _t(g["em_pi"])
+    mu_view = net.prototype_means[c].unsqueeze(0)
+    ll, log_resp = net._e_step(x, mu_view.detach(), net.prototype_covs[c].unsqueeze(0), pi_old)
+    before = net.prototype_means.detach().clone()
+    pi_new, mu_ret, var_ret = net._m_step_diversified(x, log_resp, mu_view, net.prototype_covs[c].unsqueeze(0), pi_old)
+    np.testing.assert_allclose(pi_new.cpu().numpy().reshape(-1), g["em_div_pi"].reshape(-1), rtol=1e-5)
+    assert mu_ret is mu_view
+    # the optimiser took one Adam step with the reference's gradient on class c and zero elsewhere
+    grad = np.zeros((C, K, D), np.float64)
+    grad[c] = g["em_div_grad"]
+    from oracle import mgproto_oracle as O
+    adam = O.AdamOracle((C, K, D), lr=float(g["lr"]))
+    want = adam.step(before.double().cpu().numpy(), grad)
+    np.testing.assert_allclose(net.prototype_means.detach().cpu().numpy(), want, rtol=1e-4, atol=1e-6)
+    # global_max_pooling_gmm_topT
+    B, _, H, W = g["it0_x_add"].shape
+    T = int(g["T"])
+    from mgproto_b200 import ops
+    xhat, _, nchw = ops.normalize_fwd(_t(g["it0_x_add"]), want_nchw=True)
+    prob = _t(g["it0_logp"]).exp().view(B, H, W, C, K).permute(0, 3, 4, 1, 2).contiguous()
+    vals, feats, idx = net.global_max_pooling_gmm_topT(prob, nchw, mine_T=T)
+    np.testing.assert_allclose(vals.cpu().numpy(), g["it0_topk_vals"], rtol=1e-6)
+    assert idx.dtype == torch.int64 and tuple(feats.shape) == (B, C, K, D, T)
+    sep = _separated(g["it0_topk_vals"])
+    assert (idx.view(B, C * K, T).cpu().numpy()[sep] == g["it0_topk_idx"][sep]).all()
+    f = feats.view(B, C * K, D, T).cpu().numpy()
+    xn = nchw.view(B, D, H * W).cpu().numpy()
+    ii = idx.view(B, C * K, T).cpu().numpy()
+    for b in range(B):
+        for p in range(0, C * K, 3):
+            for t in range(0, T, 2):
+                np.testing.assert_array_equal(f[b, p, :, t], xn[b, :, ii[b, p, t]])
+
+
+@pytest.mark.gpu
+def test_ood_scorer_device_side_vs_oracle_and_sklearn():
+    """configs[4] path: mgproto_b200.ood.OoDScorer (head_level0 + mgp_ood_score per batch, threshold / FPR95 / AUROC on
+    the device) against the numpy oracle's scores, numpy.percentile and sklearn's AUROC on 384 + 384 synthetic images."""
+    from sklearn.metrics import roc_auc_score
+    import mgproto_b200 as M
+    from mgproto_b200.ood import OoDScorer
+    from oracle import mgproto_oracle as O
+    C, K, D, H, W, n, bs = 12, 5, 64, 7, 7, 384, 128
+    torch.manual_seed(3)
+    net = M.MGProto(features=nn.Sequential(nn.Conv2d(3, 16, 1)), img_size=14, prototype_shape=(C * K, D, 1, 1),
+                    proto_layer_rf_info=None, num_classes=C, add_on_layers_type="regular", sz_embedding=8,
+                    mem_capacity=8, mine_K=4).to(_dev())
+    g = torch.Generator().manual_seed(9)
+    mu = net.prototype_means.detach().cpu()
+    pick = torch.randint(0, C * K, (n, H * W), generator=g)
+    x_in = (mu.view(C * K, D)[pick] + 0.1 * torch.randn(n, H * W, D, generator=g)).permute(0, 2, 1).reshape(n, D, H, W)
+    lab = (pick[:, 0] // K)
+    x_out = torch.randn(n, D, H, W, generator=g)
+    sc = OoDScorer(net)
+    for i in range(0, n, bs):
+        sc.add_in_distribution(x_in[i:i + bs].contiguous().to(_dev()), lab[i:i + bs])
+        sc.add_out_of_distribution(x_out[i:i + bs].contiguous().to(_dev()))
+    res = sc.results()
+    f64 = lambda t: t.numpy().astype(np.float64)                                  # noqa: E731
+    wt = net.last_layer.weight.detach().cpu()
+    sg = net.prototype_covs.detach().cpu()
+    ref_in = np.exp(O.head_forward(f64(x_in), f64(mu), f64(sg), f64(wt), None, 1)["logits"][:, :, 0])
+    ref_out = np.exp(O.head_forward(f64(x_out), f64(mu), f64(sg), f64(wt), None, 1)["logits"][:, :, 0])
+    np.testing.assert_allclose(torch.cat(sc.id_sum).cpu().numpy(), ref_in.sum(1), rtol=RTOL)
+    np.testing.assert_allclose(torch.cat(sc.ood_mean).cpu().numpy(), ref_out.mean(1), rtol=RTOL)
+    thr = np.percentile(ref_in.sum(1), 5)                                          # train_and_test.py:199
+    np.testing.assert_allclose(res["threshold"], thr, rtol=RTOL)
+    assert abs(res["FPR95"] - float((ref_out.mean(1) > thr).mean())) < 1e-9         # :213, :216
+    y = np.r_[np.ones(n), np.zeros(n)]
+    assert abs(res["AUROC"] - roc_auc_score(y, np.r_[ref_in.sum(1), ref_out.sum(1)])) < 1e-6
+    assert abs(res["accuracy"] - float((ref_in.argmax(1) == lab.numpy()).mean())) < 1e-9

@@ -407,6 +407,7 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")   # (NCCL prints its version banner on stdout)
         dist.init_process_group("nccl", device_id=dev)
     from mgproto_b200 import ops, parallel
     c = CFG

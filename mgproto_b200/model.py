@@ -116,7 +116,9 @@ class MGProto(nn.Module):
         self.em_n_split = 2              # row splits of the EM statistics reduction
         self.em_group = None             # torch.distributed process group of the batch-sharded replicas (parallel.py)
         self.em_shard = False            # True: shard bank rows over the ranks + all-reduce the EM statistics per loop
-        self.overlap_enqueue = True      # multi-GPU: all-gather + enqueue on a side stream, behind the backward
+        self.overlap_enqueue = False     # multi-GPU: True = all-gather + enqueue on a side stream behind the backward (measured
+                                         # slower on 2 x B200: 707 vs 640 us/step, profiles/r2_mgpu_breakdown.txt: the NCCL kernel
+                                         # and the backward kernels delay each other), False = inline on the main stream
         self._side_stream = None
         self._em_status = None           # int32[1] on the device: set by the tensor-core EM kernel if sigma was not isotropic
         self._adam_step_dev = None       # int32[1] on the device: Adam step count, advanced by update_GMM's planner

@@ -49,6 +49,7 @@ def _count(n: int):
 
 
 _op_device = None      # device of the op being issued: every tensor argument of one op must live on it
+_CHECK_ALL = os.environ.get("MGP_CHECK_DEVICES", "0") == "1"
 
 
 def _stream() -> int:
@@ -68,6 +69,16 @@ class _on_device:
 
     def __call__(self, *args, **kw):
         global _op_device
+        # fast path (one attribute read + one comparison per op): the first tensor argument's device is the current
+        # device.  Only when it is not -- or when MGP_CHECK_DEVICES=1 asks for it -- are all tensor arguments checked.
+        t0 = args[0] if args else None
+        dev = t0.device if isinstance(t0, torch.Tensor) else None
+        if dev is not None and not _CHECK_ALL and dev.type == "cuda" and dev.index == torch.cuda.current_device():
+            prev, _op_device = _op_device, dev
+            try:
+                return self.fn(*args, **kw)
+            finally:
+                _op_device = prev
         dev = None
         for a in list(args) + list(kw.values()):
             if isinstance(a, (tuple, list)):

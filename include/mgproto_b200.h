@@ -168,7 +168,7 @@ int mgp_ood_score(const float* out0, int stride_b, int stride_c, float* p_sum, f
  * lives at slot (head[c] + r) % cap, r < mem_len[c] (oldest first).  A single push larger than
  * cap keeps its first cap rows (the reference draws an unseeded random subset there).
  * updated[c] (uint8) is set for every class that received rows (ref model.py:250).
- * plan [B*K] int32 is scratch.  gt outside [0,C) skips the image. */
+ * plan: int32 scratch of mgp_bank_enqueue_plan_ints(B, C, K) elements.  gt outside [0,C) skips the image. */
 /* rows_stride / top1_stride / gt_stride: elements (fp32 / int32 / int64) between consecutive IMAGES of rows / top1 / gt;
  * 0 = dense (K*D / K / 1).  A batch-sharded run lets mgp_mined_gather write straight into packed per-image records
  * [rows K*D | top1 K | gt] that one all-gather exchanges, and mgp_bank_enqueue read the gathered records in place. */
@@ -177,6 +177,7 @@ int mgp_mined_gather(const float* xhat_nd, const int32_t* idx, const int64_t* gt
                      int T, void* stream);
 /* shadow_h / shadow_l [C,cap,D] fp16 and shadow_xx [C,cap] fp32 (all three or none): the tensor-core operand copy of
  * the bank -- hi / lo halves of 256 * row and |row|^2 -- kept in step by the scatter (see mgp_update_gmm). */
+size_t mgp_bank_enqueue_plan_ints(int B, int C, int K);
 int mgp_bank_enqueue(float* bank, int64_t* mem_len, int32_t* head, uint8_t* updated,
                      const float* rows, const int32_t* top1, const int64_t* gt, int rows_stride,
                      int top1_stride, int gt_stride, int32_t* plan,

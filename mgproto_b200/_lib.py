@@ -34,6 +34,7 @@ SIGNATURES = {
     "mgp_head_bwd": (_i, [_vp] * 11 + [_sz, _vp] + [_i] * 6 + [_vp]),
     "mgp_mined_gather": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
     "mgp_bank_enqueue": (_i, [_vp] * 7 + [_i] * 3 + [_vp] * 4 + [_i] * 5 + [_vp]),
+    "mgp_bank_enqueue_plan_ints": (_sz, [_i, _i, _i]),
     "mgp_bank_shadow_sync": (_i, [_vp] * 4 + [_i] * 3 + [_vp]),
     "mgp_bank_linearize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_em_stat_stride": (_sz, [_i, _i, _i]),

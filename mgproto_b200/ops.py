@@ -420,13 +420,14 @@ def bank_enqueue(bank, mem_len, head, updated, rows, top1, gt, shadow=None):
     rs = rows.stride(0) if B > 1 else 0
     ts = top1.stride(0) if B > 1 else 0
     gs = gt.stride(0) if B > 1 else 0
-    plan = torch.empty((B * K,), device=bank.device, dtype=torch.int32)
+    lib = _lib.load()
+    plan = torch.empty((int(lib.mgp_bank_enqueue_plan_ints(B, C, K)),), device=bank.device, dtype=torch.int32)
     sh = shadow if shadow is not None else (None, None, None)
-    check(_lib.load().mgp_bank_enqueue(bank.data_ptr(), mem_len.data_ptr(), head.data_ptr(), updated.data_ptr(),
+    check(lib.mgp_bank_enqueue(bank.data_ptr(), mem_len.data_ptr(), head.data_ptr(), updated.data_ptr(),
                                        rows.data_ptr(), top1.data_ptr(), gt.data_ptr(), int(rs), int(ts), int(gs),
                                        plan.data_ptr(), _p(sh[0]), _p(sh[1]), _p(sh[2]), B, C, K, D, cap, _stream()),
           "mgp_bank_enqueue")
-    _count(2)
+    _count(3)
 
 
 @_on_device

@@ -390,6 +390,7 @@ def main():
     ap.add_argument("--math", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference_gpu_eager leg")
+    ap.add_argument("--no-ood", action="store_true", help="skip the configs[4] OoD-scoring throughput leg")
     ap.add_argument("--reps", type=int, default=10, help="repetitions of the --steps block (median reported)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -630,6 +631,48 @@ def main():
                         "fp16 hi/lo shadow (same bytes as the fp32 bank) is re-read per EM loop, L2-resident after the first"}
         except Exception as ex:  # noqa: BLE001 -- an auxiliary figure must never cost the bench line
             extra["roofline_step_update_gmm"] = {"error": str(ex)[:200]}
+
+    # ---- BASELINE.json configs[4]: OoD log-likelihood scoring, 50k in-distribution + 50k OoD synthetic images ----
+    if rank == 0 and not args.no_ood:
+        try:
+            from mgproto_b200.ood import OoDScorer
+            n_each, bs = 50000, 500
+            g5 = torch.Generator(device=dev).manual_seed(5)
+            protos = net.prototype_means.detach().reshape(-1, D)
+
+            def batch_in():
+                pick = torch.randint(0, protos.shape[0], (bs, HW), device=dev, generator=g5)
+                v = protos[pick] + 0.1 * torch.randn(bs, HW, D, device=dev, generator=g5)
+                return v.permute(0, 2, 1).reshape(bs, D, H, Wd).contiguous()
+
+            def batch_out():
+                return torch.randn(bs, D, H, Wd, device=dev, generator=g5)
+
+            pool_in = [batch_in() for _ in range(4)]               # 4 x 49 MB of each kind rotate (> L2 together)
+            pool_out = [batch_out() for _ in range(4)]
+            sc = OoDScorer(net)
+            sc.add_in_distribution(pool_in[0])
+            sc.add_out_of_distribution(pool_out[0])
+            sc = OoDScorer(net)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(n_each // bs):
+                sc.add_in_distribution(pool_in[i % 4])
+                sc.add_out_of_distribution(pool_out[i % 4])
+            res = sc.results()
+            e1.record()
+            torch.cuda.synchronize()
+            t_ood = e0.elapsed_time(e1) / 1e3
+            extra["ood_scoring"] = {
+                "workload": "BASELINE.json configs[4]: 50k in-distribution (random prototype + 0.1 randn per patch) + 50k OoD "
+                            "(random) synthetic feature maps, batches of %d: head_level0 + mgp_ood_score per batch, 5th-percentile "
+                            "threshold / FPR95 / AUROC on the device (mgproto_b200.ood.OoDScorer)" % bs,
+                "images_per_s": 2 * n_each / t_ood, "seconds": t_ood, "AUROC": res["AUROC"], "FPR95": res["FPR95"],
+                "threshold": res["threshold"],
+                "parity": "scores / threshold / FPR95 / AUROC against the oracle, numpy.percentile and sklearn at n = 384 + 384: "
+                          "tests/test_gpu_parity.py::test_ood_scorer_device_side_vs_oracle_and_sklearn"}
+        except Exception as ex:  # noqa: BLE001
+            extra["ood_scoring"] = {"error": str(ex)[:200]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

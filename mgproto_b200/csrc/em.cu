@@ -25,6 +25,7 @@ namespace cg = cooperative_groups;
 
 int mgp_opt_em_fused();   // abi.cu
 int mgp_opt_em_tc();      // abi.cu
+int mgp_opt_em_pipe();    // abi.cu
 // em_tc.cu
 bool mgp_em_tc_supported(int K, int D, int cap);
 int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* shadow_xx, const float* bias_corr, const int32_t* order,
@@ -38,20 +39,21 @@ using namespace mgp_em;
 __global__ void __launch_bounds__(1024)
 em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_len, int32_t* __restrict__ order,
                int32_t* __restrict__ sched, int32_t* __restrict__ adam_step, int step0, int C, int cap, int num_em_loop,
-               AdamCfg adam, float* __restrict__ bias_corr) {
+               AdamCfg adam, float* __restrict__ bias_corr, int32_t* __restrict__ clist = nullptr) {
     __shared__ int s_plan[2];
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const bool act = updated[c] != 0 && mem_len[c] >= (int64_t)cap;   // ref model.py:283, :289
-        order[c] = act ? 1 : 0;
-    }
+    __shared__ int s_wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    auto active = [&](int c) { return c < C && updated[c] != 0 && mem_len[c] >= (int64_t)cap; };   // ref model.py:283, :289
+    // pass 1: how many classes are active
+    int cnt = 0;
+    for (int c = tid; c < C; c += blockDim.x) cnt += active(c) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_wsum[warp] = cnt;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         int r = 0;
-        for (int c = 0; c < C; ++c) {
-            const int a = order[c];
-            order[c] = a ? r : -1;
-            r += a;
-        }
+        for (int w = 0; w < nwarp; ++w) r += s_wsum[w];
         sched[0] = r;
         const int s0 = adam_step ? adam_step[0] : step0;
         sched[1] = s0;
@@ -59,7 +61,30 @@ em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_le
         s_plan[0] = r; s_plan[1] = s0;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) updated[c] = 0;      // ref model.py:287, :301
+    // pass 2: order[c] = rank among the active (ascending id) or -1; clist = the classes in launch order, the active ones first
+    const int r_total = s_plan[0];
+    int base = 0;
+    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+        const int c = c0 + tid;
+        const bool act = active(c);
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, chunk = 0;
+        for (int w = 0; w < nwarp; ++w) {
+            const int v = s_wsum[w];
+            before += (w < warp) ? v : 0;
+            chunk += v;
+        }
+        const int rank = base + before + __popc(bal & ((1u << lane) - 1u));   // active classes with a smaller id
+        if (c < C) {
+            order[c] = act ? rank : -1;
+            if (clist) clist[act ? rank : r_total + (c - rank)] = c;
+        }
+        base += chunk;
+        __syncthreads();
+    }
+    for (int c = tid; c < C; c += blockDim.x) updated[c] = 0;             // ref model.py:287, :301
     if (bias_corr) {
         // Step-dependent factors of this call's Adam steps s0+1 .. s0+n (n = r*L), evaluated ONCE here in double (torch:
         // Python doubles, narrowed last) instead of per class in the EM kernel:
@@ -1438,7 +1463,7 @@ static bool em_tc_applies(int K, int D, int cap, int have_shadow_iso) {
 }
 
 extern "C" int mgp_update_gmm_launches(int K, int D, int cap, int num_em_loop, int have_shadow_iso) {
-    if (em_tc_applies(K, D, cap, have_shadow_iso)) return 2;
+    if (em_tc_applies(K, D, cap, have_shadow_iso)) return (D == 128 && mgp_opt_em_pipe()) ? 3 : 2;   // plan + kernel(s)
     return em_fused_applies(K, D, cap) ? 2 : 3 + 2 * num_em_loop;
 }
 
@@ -1465,10 +1490,11 @@ extern "C" int mgp_update_gmm(const float* bank, const void* shadow_h, const voi
     if (rc != MGP_OK) return rc;
 #ifdef MGP_WITH_TC
     if (shadow_h && shadow_l && shadow_xx && status && em_tc_applies(K, D, cap, sigma_iso) &&
-        (size_t)5 * num_em_loop * C + 3 <= (size_t)C * n_split * mgp_em_stat_stride(K, D, 0)) {
+        (size_t)5 * num_em_loop * C + 4 + C <= (size_t)C * n_split * mgp_em_stat_stride(K, D, 0)) {
         // tensor-core path: the planner also tabulates the steps' Adam bias corrections into the (otherwise unused) stats scratch
         em_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(updated, mem_len, order, sched, adam_step, 0, C, cap, num_em_loop,
-                                                             make_adam(lr, beta1, beta2, adam_eps), stats);
+                                                             make_adam(lr, beta1, beta2, adam_eps), stats,
+                                                             reinterpret_cast<int32_t*>(stats + (size_t)5 * num_em_loop * C + 4));
         MGP_CHECK_LAUNCH();
         return mgp_em_tc_launch(shadow_h, shadow_l, shadow_xx, stats, order, sched, mu, sigma, weight_cp, exp_avg, exp_avg_sq,
                                 status, num_em_loop, alpha, lr, beta1, beta2, adam_eps, tau, lamda, C, K, D, cap,

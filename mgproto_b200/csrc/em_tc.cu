@@ -43,6 +43,8 @@ struct EmTcParams {
     const float* bc;              // planner tables: [2 n] Adam bias corrections of steps step0+1.., then b1^i, b2^(i/2), b2^i for i <= n = L * n_active
     const int32_t* order;
     const int32_t* sched;
+    const int32_t* clist;         // planner: classes in launch order, active first (stats scratch at 5 L C + 4)
+    int pipe_max;                 // the pipelined kernel runs iff n_active <= pipe_max (0: never)
     float* mu;
     const float* sigma;
     float* weight;
@@ -61,30 +63,50 @@ struct EmTcParams {
         if (prm.prof && blockIdx.x == prm.prof_class && (ctr) < 64) prm.prof[(ctr) * 8 + (ph)] = clock64();  \
     } while (0)
 
-template <int D, int KT>
-__global__ void __launch_bounds__(256, (D == 128) ? 2 : 1)
+// PIPE (D = 128): three row-tile buffers, two E-step accumulators and two R buffers, so that the TMA load of tile t+1,
+// the E-step MMAs of tile t and the statistics MMAs of tile t-1 overlap the soft-max epilogue (one CTA per SM; the
+// planner's class list puts the active classes first).  !PIPE (D = 256: one 128 KB tile buffer fits): serial per tile.
+// Sum V = 32 R values per lane across the warp with V - R shuffles (a butterfly that halves the live set each round)
+// instead of 5 V: afterwards a[i], i < R, holds the warp total of entry R * lane + i.
+template <int V>
+__device__ __forceinline__ void warp_multi_reduce(float (&a)[V], int lane) {
+    static_assert(V % 32 == 0, "V must be a multiple of the warp size");
+#pragma unroll
+    for (int off = 16, n = V / 2; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = up ? a[i] : a[i + n], keep = up ? a[i + n] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+template <int D, int KT, bool PIPE>
+__global__ void __launch_bounds__(256, (D == 128 && !PIPE) ? 2 : 1)
 em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const EmTcParams prm) {
     constexpr int NCH = D / 64;                    // 64-element (128 B) chunks along d
     constexpr uint32_t CH_BYTES = TR * 128;        // one [128 rows x 64] fp16 block
     constexpr uint32_t X_BYTES = NCH * CH_BYTES;   // hi (lo follows)
     constexpr int DB = D / 128;                    // 128-wide d blocks (statistics accumulators)
     constexpr int OWN = D;                         // threads owning mean/moment elements: thread d <-> (k, d) for all k
-    constexpr int TMEM_COLS = (D == 128) ? 64 : 128;    // 32 (E-step: hi.hi + lo.hi | hi.lo) + DB * 32 (statistics)
+    constexpr int TMEM_COLS = (D == 128 && !PIPE) ? 64 : 128;   // (PIPE: 2 x) 32 (E-step: hi.hi + lo.hi | hi.lo) + DB * 32 (statistics)
     constexpr int ISSUER = 128;                    // the TMA / MMA issuing thread: lane 0 of warp 4 (warps 0-3 run the E-step epilogue)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* bp = smem_raw + (base - raw);
     // carve-up (bytes from `base`)
-    const uint32_t o_xh = 0, o_xl = X_BYTES;
+    constexpr int NXBUF = PIPE ? 3 : 1, NRBUF = PIPE ? 2 : 1;
+    const uint32_t o_xh = 0, o_xl = X_BYTES;                               // buffer b: + b * 2 * X_BYTES
     // means operand A and responsibilities R: per 64-wide K chunk one [32 rows x 128 B] block, rows 0-15 = hi,
     // rows 16-31 = lo, so ONE N = 32 MMA multiplies the row tile's hi half with both and an N = 16 MMA adds lo x hi
-    const uint32_t o_a = 2 * X_BYTES;                                     // [NCH][32][128 B]
-    const uint32_t o_r = o_a + NCH * 4096;                                // [2 (64-row chunks)][32][128 B]
-    const uint32_t o_misc = o_r + 8192;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bp + o_misc);            // tma, estep, stats (+ TMEM slot)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-    float* s_e = reinterpret_cast<float*>(bars + 4);                      // [KT][KT]
+    const uint32_t o_a = NXBUF * 2 * X_BYTES;                             // [NCH][32][128 B]
+    const uint32_t o_r = o_a + NCH * 4096;                                // NRBUF x [2 (64-row chunks)][32][128 B]
+    const uint32_t o_misc = o_r + NRBUF * 8192;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bp + o_misc);            // !PIPE: tma, estep, stats | PIPE: xfull[3] xfree[3] efull[2] rfull[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    float* s_e = reinterpret_cast<float*>(bars + 12);                     // [KT][KT]
     float* s_c = s_e + KT * KT;                                           // [TAB]
     float* s_d = s_c + TAB;                                               // [TAB]
     float* s_red = s_d + TAB;                                             // [8] + [8][16]
@@ -95,12 +117,23 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     float* s_s0 = s_cst + 16;                                             // [16]
     float* s_misc = s_s0 + 16;                                            // [8]: replay sums T1..T3, min d; operand scale; moment decays
     constexpr int NPAIR = KT * (KT - 1) / 2;
-    float* s_pair = s_misc + 8;                                           // [8 warps][NPAIR] partial |mu_i - mu_j|^2
+    // per-warp partials of the loop top: |mu_i - mu_j|^2 for the NPAIR pairs, then |mu_k|^2 for the KT components
+    constexpr bool MULTI = (NPAIR + KT) <= 64;                            // one transposing reduction (warp_multi_reduce)
+    constexpr int PV = MULTI ? 32 * ((NPAIR + KT + 31) / 32) : NPAIR + KT;
+    float* s_pair = s_misc + 8;                                           // [8 warps][PV]
     const uint32_t bar_tma = smem_u32(bars), bar_e = bar_tma + 8, bar_s = bar_tma + 16;
 
-    const int c = blockIdx.x;
-    const int ord = prm.order[c];
     const int n_active = prm.sched[0], step0 = prm.sched[1];
+    // PIPE: one CTA per SM, so the planner's class list (active classes first, in order) decides who starts first
+    // Launch regimes (both kernels are enqueued when D = 128; the planner's count decides on the device):
+    //   n_active <= pipe_max (one CTA per SM covers every active class) -> the pipelined kernel, else the serial one.
+    if (PIPE ? (n_active > prm.pipe_max) : (n_active <= prm.pipe_max)) return;
+    // PIPE: CTA b < n_active runs active class clist[b]; its idle warps also take the inactive classes clist[n_active + b
+    // (+ n_active)], so that those do not queue behind the 225 KB CTAs; inactive classes beyond 2 n_active get own CTAs
+    constexpr int ABSORB = 2;
+    if (PIPE && (int)blockIdx.x >= n_active && (int)blockIdx.x - n_active < ABSORB * n_active) return;
+    const int c = PIPE ? prm.clist[blockIdx.x] : (int)blockIdx.x;
+    const int ord = prm.order[c];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = prm.K, cap = prm.cap, L = prm.num_em_loop, P = prm.C * K, KD = K * D;
     const AdamCfg& adam = prm.adam;
@@ -130,68 +163,99 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     const float* t_b1 = prm.bc + 2 * n_steps;
     const float* t_b2h = t_b1 + (n_steps + 1);
     const float* t_b2 = t_b2h + (n_steps + 1);
-    auto replay = [&](int first, int count) {
+    // (a) one warp: the replay's block-wide scalars T1..T3 and min d_s
+    auto replay_sums = [&](int first, int count, int ns, bool tail, float& T1, float& T2, float& T3, float& dmin_out) {
+        const int i0 = first - step0;                       // table index of step first+1
+        double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        float dmin = INFINITY;
+        for (int s = lane + 1; s <= ns + (tail ? 1 : 0); s += 32) {
+            float cs, ds;
+            if (s <= ns) {
+                cs = __ldg(prm.bc + 2 * (i0 + s - 1)) * __ldg(t_b1 + s);
+                ds = __ldg(t_b2h + s) / __ldg(prm.bc + 2 * (i0 + s - 1) + 1);
+            } else {                                    // steps ns+1 .. count as one geometric term (em_common.cuh)
+                const float geo = __ldg(t_b1 + ns + 1) * (1.0f - __ldg(t_b1 + (count - ns))) / (float)(1.0 - adam.beta1);
+                const int ss = min(count, ns + 1 + (int)(adam.beta1 / (1.0 - adam.beta1)));
+                cs = __ldg(prm.bc + 2 * (i0 + ns)) * geo;
+                ds = __ldg(t_b2h + ss) / __ldg(prm.bc + 2 * (i0 + ss - 1) + 1);
+            }
+            const double c = (double)cs, r = 1.0 / (double)ds;
+            t1 += c * r; t2 += c * r * r; t3 += c * r * r * r;
+            dmin = fminf(dmin, ds);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+            t3 += __shfl_xor_sync(0xffffffffu, t3, o);
+            dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        }
+        T1 = (float)t1; T2 = (float)t2; T3 = (float)t3; dmin_out = dmin;
+    };
+    // (b) one element: p after the `count` zero-gradient steps (the moments decay separately)
+    auto replay_elem = [&](float p, float m, float v, int first, int count, int ns, bool tail, float T1, float T2, float T3,
+                           float dmin) -> float {
+        const float a = sqrtf(v);
+        if (a * dmin > 1000.0f * adam.epsf) {
+            const float inv = 1.0f / a;
+            const float e = adam.epsf * inv;
+            return fmaf(-m * inv, fmaf(-e, fmaf(-e, T3, T2), T1), p);
+        }
+        if (m != 0.f) {                                     // tiny second moment (fresh optimiser): term by term
+            const int i0 = first - step0;
+            for (int s = 1; s <= ns; ++s) {
+                const float cs = __ldg(prm.bc + 2 * (i0 + s - 1)) * __ldg(t_b1 + s);
+                const float ds = __ldg(t_b2h + s) / __ldg(prm.bc + 2 * (i0 + s - 1) + 1);
+                p = fmaf(-cs * m, 1.0f / fmaf(a, ds, adam.epsf), p);
+            }
+            if (tail) {
+                const float geo = __ldg(t_b1 + ns + 1) * (1.0f - __ldg(t_b1 + (count - ns))) / (float)(1.0 - adam.beta1);
+                const int ss = min(count, ns + 1 + (int)(adam.beta1 / (1.0 - adam.beta1)));
+                const float cs = __ldg(prm.bc + 2 * (i0 + ns)) * geo;
+                const float ds = __ldg(t_b2h + ss) / __ldg(prm.bc + 2 * (i0 + ss - 1) + 1);
+                p = fmaf(-cs * m, 1.0f / fmaf(a, ds, adam.epsf), p);
+            }
+        }
+        return p;
+    };
+    // the sums of a replay, by ONE warp, into sums[0..3] (shared memory; the caller's next block barrier publishes them)
+    auto replay_prepare = [&](int first, int count, float* sums) {
+        if (count <= 0) return;
+        const int ns = replay_explicit_steps(count, first, (float)adam.beta1);
+        float T1, T2, T3, dmin;
+        replay_sums(first, count, ns, count > ns, T1, T2, T3, dmin);
+        if (lane == 0) { sums[0] = T1; sums[1] = T2; sums[2] = T3; sums[3] = dmin; }
+    };
+    auto replay = [&](int first, int count, const float* sums) {
         if (count <= 0) return;
         const int ns = replay_explicit_steps(count, first, (float)adam.beta1);
         const bool tail = count > ns;
-        const int i0 = first - step0;                       // table index of step first+1
-        __syncthreads();
-        if (warp == 0) {
-            double t1 = 0.0, t2 = 0.0, t3 = 0.0;
-            float dmin = INFINITY;
-            for (int s = lane + 1; s <= ns + (tail ? 1 : 0); s += 32) {
-                float cs, ds;
-                if (s <= ns) {
-                    cs = __ldg(prm.bc + 2 * (i0 + s - 1)) * __ldg(t_b1 + s);
-                    ds = __ldg(t_b2h + s) / __ldg(prm.bc + 2 * (i0 + s - 1) + 1);
-                } else {                                    // steps ns+1 .. count as one geometric term (em_common.cuh)
-                    const float geo = __ldg(t_b1 + ns + 1) * (1.0f - __ldg(t_b1 + (count - ns))) / (float)(1.0 - adam.beta1);
-                    const int ss = min(count, ns + 1 + (int)(adam.beta1 / (1.0 - adam.beta1)));
-                    cs = __ldg(prm.bc + 2 * (i0 + ns)) * geo;
-                    ds = __ldg(t_b2h + ss) / __ldg(prm.bc + 2 * (i0 + ss - 1) + 1);
-                }
-                const double c = (double)cs, r = 1.0 / (double)ds;
-                t1 += c * r; t2 += c * r * r; t3 += c * r * r * r;
-                dmin = fminf(dmin, ds);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-                t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-                t3 += __shfl_xor_sync(0xffffffffu, t3, o);
-                dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-            }
-            if (lane == 0) { s_misc[0] = (float)t1; s_misc[1] = (float)t2; s_misc[2] = (float)t3; s_misc[3] = dmin; }
-        }
-        __syncthreads();
         if (own) {
-            const float T1 = s_misc[0], T2 = s_misc[1], T3 = s_misc[2], dmin = s_misc[3];
+            const float T1 = sums[0], T2 = sums[1], T3 = sums[2], dmin = sums[3];
 #pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                const float a = sqrtf(v_[k]);
-                if (a * dmin > 1000.0f * adam.epsf) {
-                    const float inv = 1.0f / a;
-                    const float e = adam.epsf * inv;
-                    p_[k] = fmaf(-m_[k] * inv, fmaf(-e, fmaf(-e, T3, T2), T1), p_[k]);
-                } else if (m_[k] != 0.f) {                  // tiny second moment (fresh optimiser): term by term
-                    for (int s = 1; s <= ns; ++s) {
-                        const float cs = __ldg(prm.bc + 2 * (i0 + s - 1)) * __ldg(t_b1 + s);
-                        const float ds = __ldg(t_b2h + s) / __ldg(prm.bc + 2 * (i0 + s - 1) + 1);
-                        p_[k] = fmaf(-cs * m_[k], 1.0f / fmaf(a, ds, adam.epsf), p_[k]);
-                    }
-                    if (tail) {
-                        const float geo = __ldg(t_b1 + ns + 1) * (1.0f - __ldg(t_b1 + (count - ns))) / (float)(1.0 - adam.beta1);
-                        const int ss = min(count, ns + 1 + (int)(adam.beta1 / (1.0 - adam.beta1)));
-                        const float cs = __ldg(prm.bc + 2 * (i0 + ns)) * geo;
-                        const float ds = __ldg(t_b2h + ss) / __ldg(prm.bc + 2 * (i0 + ss - 1) + 1);
-                        p_[k] = fmaf(-cs * m_[k], 1.0f / fmaf(a, ds, adam.epsf), p_[k]);
-                    }
-                }
-            }
+            for (int k = 0; k < KT; ++k) p_[k] = replay_elem(p_[k], m_[k], v_[k], first, count, ns, tail, T1, T2, T3, dmin);
         }
         const float mdec = __ldg(t_b1 + count), vdec = __ldg(t_b2 + count);   // the moments decay by the full count
 #pragma unroll
         for (int k = 0; k < KT; ++k) { m_[k] *= mdec; v_[k] *= vdec; }
+    };
+    // an inactive class only takes everybody's zero-gradient steps: warps [w0, w0 + nw) of this CTA, straight from / to
+    // global memory (PIPE: done by the warps that idle during an active class's first tile loop)
+    auto replay_inactive = [&](int ci, int w0, int nw) {
+        const int count = L * n_active;
+        if (count <= 0) return;
+        const int ns = replay_explicit_steps(count, step0, (float)adam.beta1);
+        const bool tail = count > ns;
+        float T1, T2, T3, dmin;
+        replay_sums(step0, count, ns, tail, T1, T2, T3, dmin);            // (every warp for itself: no block barrier here)
+        const float mdec = __ldg(t_b1 + count), vdec = __ldg(t_b2 + count);
+        for (int o = (warp - w0) * 32 + lane; o < KD; o += nw * 32) {
+            const size_t g = (size_t)ci * KD + o;
+            const float p = prm.mu[g], m = prm.exp_avg[g], v = prm.exp_avg_sq[g];
+            prm.mu[g] = replay_elem(p, m, v, step0, count, ns, tail, T1, T2, T3, dmin);
+            prm.exp_avg[g] = m * mdec;
+            prm.exp_avg_sq[g] = v * vdec;
+        }
     };
     auto write_back = [&]() {
         if (!own) return;
@@ -204,17 +268,27 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     };
 
     if (ord < 0) {                                   // inactive class: it only takes everybody's zero-gradient steps
-        replay(step0, L * n_active);
+        if (warp == 0) replay_prepare(step0, L * n_active, s_misc);
+        __syncthreads();
+        replay(step0, L * n_active, s_misc);
         write_back();
         return;
     }
+    // the two replays' block-wide sums depend on the plan only: two otherwise idle warps evaluate them under the set-up
+    if (warp == 7) replay_prepare(step0, L * ord, s_misc);
+    if (warp == 6) replay_prepare(step0 + L * (ord + 1), L * (n_active - ord - 1), s_misc + 4);
 
     if (tid == 0) MGP_PROF(63, 1);
     // ---- set-up: barriers, TMEM, sigma-derived constants, zeroed operand tiles
     if (tid == 0) {
-        mbar_init(bar_tma, 1);
-        mbar_init(bar_e, 1);
-        mbar_init(bar_s, 1);
+        if (PIPE) {
+            for (int i = 0; i < 3; ++i) { mbar_init(bar_tma + 8u * i, 1); mbar_init(bar_tma + 8u * (3 + i), 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(bar_tma + 8u * (6 + i), 1); mbar_init(bar_tma + 8u * (8 + i), 4); }
+        } else {
+            mbar_init(bar_tma, 1);
+            mbar_init(bar_e, 1);
+            mbar_init(bar_s, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -223,7 +297,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     }
     bool same = true;
     for (int i = tid; i < KD; i += 256) same = same && (sg_c[i] == sg_c[(i / D) * D]);
-    for (uint32_t i = tid * 16u; i < NCH * 4096u + 8192u; i += 256u * 16u)             // A and R blocks: rows >= K stay zero
+    for (uint32_t i = tid * 16u; i < NCH * 4096u + NRBUF * 8192u; i += 256u * 16u)     // A and R blocks: rows >= K stay zero
         *reinterpret_cast<uint4*>(bp + o_a + i) = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < KT * KT; i += 256) s_e[i] = 0.f;
     if (tid < 16) {
@@ -246,7 +320,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         return;
     }
     if (tid == 0) MGP_PROF(63, 2);
-    replay(step0, L * ord);
+    replay(step0, L * ord, s_misc);
     if (tid == 0) MGP_PROF(63, 3);
 
     const int ntiles = (cap + TR - 1) / TR;
@@ -258,7 +332,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     // statistics: A = X^T (MN-major), B = [R hi ; R lo] (K-major)
     const uint32_t idesc_s32 = umma_idesc_f16(128, 2 * NK, 1, 0), idesc_s16 = umma_idesc_f16(128, NK, 1, 0);
     const uint32_t d_e = tmem_base;                                  // [128 rows x (16 hi.hi + lo.hi | 16 hi.lo)]
-    const uint32_t d_s = tmem_base + 32;                             // DB x [128 d x 32], same column split
+    const uint32_t d_s = tmem_base + (PIPE ? 64 : 32);               // DB x [128 d x 32], same column split
     uint32_t tile_ctr = 0;                                           // tiles issued so far (mbarrier phases)
 
     auto load_tile = [&](int t) {                                    // issuer only: one 128-row tile, hi + lo, into the X buffer
@@ -273,34 +347,47 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     for (int loop = 0; loop < L; ++loop) {
         // ---- means operand, |mu_k|^2, diversity kernel from the current means (all from the owners' registers)
         float amax = 0.f;
-        float mmp[KT];
+        if (own) {                                                   // (warp-uniform: OWN is a multiple of 32)
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            mmp[k] = 0.f;
-            if (own && k < K) {
-                amax = fmaxf(amax, fabsf(2.0f * s_w[k] * p_[k]));
-                mmp[k] = p_[k] * p_[k];
+            for (int k = 0; k < KT; ++k)
+                if (k < K) amax = fmaxf(amax, fabsf(2.0f * s_w[k] * p_[k]));
+            amax = warp_max(amax);
+            // this thread's dimension of |mu_i - mu_j|^2 (ref utils/helpers.py:13-14; i < j) and of |mu_k|^2, summed over the warp
+            if constexpr (MULTI) {
+                float a[PV];
+                int pi = 0;
+#pragma unroll
+                for (int i = 0; i < KT; ++i)
+#pragma unroll
+                    for (int j = i + 1; j < KT; ++j, ++pi) {
+                        const float df = (j < K) ? p_[i] - p_[j] : 0.f;
+                        a[pi] = df * df;
+                    }
+#pragma unroll
+                for (int k = 0; k < KT; ++k) a[NPAIR + k] = (k < K) ? p_[k] * p_[k] : 0.f;
+#pragma unroll
+                for (int i = NPAIR + KT; i < PV; ++i) a[i] = 0.f;
+                warp_multi_reduce<PV>(a, lane);                      // lane l now holds entries (PV/32) l + i
+#pragma unroll
+                for (int i = 0; i < PV / 32; ++i) s_pair[warp * PV + (PV / 32) * lane + i] = a[i];
+            } else {
+                int pi = 0;
+#pragma unroll
+                for (int i = 0; i < KT; ++i)
+#pragma unroll
+                    for (int j = i + 1; j < KT; ++j, ++pi) {
+                        const float df = (j < K) ? p_[i] - p_[j] : 0.f;
+                        const float t = warp_sum(df * df);
+                        if (lane == 0) s_pair[warp * PV + pi] = t;
+                    }
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    const float t = warp_sum((k < K) ? p_[k] * p_[k] : 0.f);
+                    if (lane == 0) s_pair[warp * PV + NPAIR + k] = t;
+                }
             }
         }
-        amax = warp_max(amax);
-#pragma unroll
-        for (int k = 0; k < KT; ++k) mmp[k] = warp_sum(mmp[k]);
-        if (lane == 0) {
-            s_red[warp] = amax;
-#pragma unroll
-            for (int k = 0; k < KT; ++k) s_red[8 + warp * 16 + k] = mmp[k];
-        }
-        {   // |mu_i - mu_j|^2 (ref utils/helpers.py:13-14): this thread's dimension, reduced over the warp, i < j
-            int pi = 0;
-#pragma unroll
-            for (int i = 0; i < KT; ++i)
-#pragma unroll
-                for (int j = i + 1; j < KT; ++j, ++pi) {
-                    const float df = (own && j < K) ? p_[i] - p_[j] : 0.f;
-                    const float t = warp_sum(df * df);
-                    if (lane == 0) s_pair[warp * NPAIR + pi] = t;
-                }
-        }
+        if (lane == 0) s_red[warp] = amax;
         __syncthreads();
         float a_scale;
         {
@@ -314,7 +401,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         if (tid < K) {
             float mm = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) mm += s_red[8 + w8 * 16 + tid];
+            for (int w8 = 0; w8 < OWN / 32; ++w8) mm += s_pair[w8 * PV + NPAIR + tid];
             s_cst[tid] = -s_ls[tid] + logf(s_pi[tid] + EM_EPS) - 0.5f * s_w[tid] * mm;   // ref :316, :323-336
         }
         if (tid >= 32 && tid < 32 + NPAIR) {                         // exp(-|mu_i - mu_j|^2), ref model.py:390-392
@@ -324,7 +411,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
             const int j = i + 1 + rem;
             float t = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < OWN / 32; ++w8) t += s_pair[w8 * NPAIR + pr];
+            for (int w8 = 0; w8 < OWN / 32; ++w8) t += s_pair[w8 * PV + pr];
             const float e = (j < K) ? expf(-t) : 0.f;
             s_e[i * KT + j] = e;
             s_e[j * KT + i] = e;
@@ -347,6 +434,138 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         for (int k = 0; k < KT; ++k) s0[k] = 0.f;
         const float inv_a = 1.0f / (a_scale * SX);
 
+        if constexpr (PIPE) {
+            // mbarriers: xfull[b] tile landed in buffer b | xfree[b] the statistics MMAs reading buffer b (and the R buffer
+            // they used) have retired | efull[e] E-step accumulator e complete | rfull[e] soft-max wrote R buffer e.
+            // Global tile counter g: row-tile buffer g % 3, accumulator / R buffer g & 1; every barrier completes exactly
+            // once per tile that uses its buffer, so its phase parity is (g / 3) & 1 resp. (g / 2) & 1.
+            auto XFULL = [&](uint32_t b) { return bar_tma + 8u * b; };
+            auto XFREE = [&](uint32_t b) { return bar_tma + 8u * (3 + b); };
+            auto EFULL = [&](uint32_t e) { return bar_tma + 8u * (6 + e); };
+            auto RFULL = [&](uint32_t e) { return bar_tma + 8u * (8 + e); };
+            const uint32_t g0 = tile_ctr;
+            auto load_tile_p = [&](int t, uint32_t g) {              // issuer: tile t of this class -> buffer g % 3
+                const uint32_t b = g % 3u;
+                if (g >= 3) mbar_wait(XFREE(b), ((g - 3) / 3u) & 1u);   // the previous tile in this buffer has been consumed
+                mbar_expect_tx(XFULL(b), 2 * X_BYTES);
+                const int row0 = c * cap + t * TR;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    tma_load_2d(base + b * 2 * X_BYTES + o_xh + ch * CH_BYTES, &map_h, ch * 64, row0, XFULL(b));
+                    tma_load_2d(base + b * 2 * X_BYTES + o_xl + ch * CH_BYTES, &map_l, ch * 64, row0, XFULL(b));
+                }
+            };
+            auto stats_mma = [&](int t, uint32_t g) {                // issuer: D_s += X(g)^T . [R_hi ; R_lo](g)
+                const uint32_t xb = base + (g % 3u) * 2 * X_BYTES, rb = base + o_r + (g & 1u) * 8192u;
+                mbar_wait(RFULL(g & 1u), (g >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < TR / 16; ++ks) {
+                    const uint32_t xo = (uint32_t)ks * 2048u;        // 16 rows x 128 B
+                    const uint64_t bd = umma_desc(rb + (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u);
+                    tc_mma_f16(d_s, umma_desc_mn(xb + o_xh + xo, CH_BYTES, 1024u), bd, idesc_s32, (t | ks) != 0);
+                    tc_mma_f16(d_s, umma_desc_mn(xb + o_xl + xo, CH_BYTES, 1024u), bd, idesc_s16, 1u);
+                }
+                tc_commit(XFREE(g % 3u));
+                MGP_PROF(g, 5);
+            };
+            if (warp == ISSUER / 32) {
+                if (tid == ISSUER) {
+                    if (loop == 0) load_tile_p(0, g0);               // (later loops: prefetched under the previous loop's tail)
+                    for (int t = 0; t < ntiles; ++t) {
+                        const uint32_t g = g0 + t;
+                        MGP_PROF(g, 0);
+                        if (t + 1 < ntiles) load_tile_p(t + 1, g + 1);
+                        mbar_wait(XFULL(g % 3u), (g / 3u) & 1u);
+                        MGP_PROF(g, 1);
+                        tc_fence_after();
+                        const uint32_t xb = base + (g % 3u) * 2 * X_BYTES, de = d_e + (g & 1u) * 32u;
+#pragma unroll
+                        for (int ks = 0; ks < D / 16; ++ks) {
+                            const uint32_t xo = (uint32_t)(ks >> 2) * CH_BYTES + (uint32_t)(ks & 3) * 32u;
+                            const uint64_t bd = umma_desc(base + o_a + (uint32_t)(ks >> 2) * 4096u + (uint32_t)(ks & 3) * 32u);
+                            tc_mma_f16(de, umma_desc(xb + o_xh + xo), bd, idesc_e32, ks != 0);
+                            tc_mma_f16(de, umma_desc(xb + o_xl + xo), bd, idesc_e16, 1u);
+                        }
+                        tc_commit(EFULL(g & 1u));
+                        MGP_PROF(g, 2);
+                        if (t >= 1) stats_mma(t - 1, g - 1);
+                    }
+                    stats_mma(ntiles - 1, g0 + ntiles - 1);
+                    if (loop + 1 < L) load_tile_p(0, g0 + ntiles);   // the next loop's first tile, under this loop's tail
+                }
+                __syncwarp();
+            }
+            if (warp >= 5 && loop == 0) {                            // idle here: the absorbed inactive classes
+                for (int j = (int)blockIdx.x; j < ABSORB * n_active && n_active + j < prm.C; j += n_active)
+                    replay_inactive(prm.clist[n_active + j], 5, 3);
+            }
+            if (warp < 4) {
+                for (int t = 0; t < ntiles; ++t) {
+                    const uint32_t g = g0 + t;
+                    const int row = t * TR + tid;
+                    const bool valid = row < cap;
+                    const float xxv = valid ? __ldg(prm.xx + (size_t)c * cap + row) : 0.f;
+                    mbar_wait(EFULL(g & 1u), (g >> 1) & 1u);
+                    if (tid == 0) MGP_PROF(g, 3);
+                    tc_fence_after();
+                    uint32_t q[16], q1[16];
+                    const uint32_t de = d_e + (g & 1u) * 32u + ((uint32_t)(warp * 32) << 16);
+                    tmem_ld16(de, q);
+                    tmem_ld16(de + 16, q1);
+                    tmem_ld_wait();
+                    float wl[KT], mx = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < KT; ++k) {
+                        const float acc = __uint_as_float(q[k]) + __uint_as_float(q1[k]);
+                        const float qq = fmaf(s_w[k], xxv, acc * inv_a);
+                        wl[k] = (k < K) ? s_cst[k] - 0.5f * qq : -INFINITY;             // lp + log(pi + eps)  (ref :316)
+                        mx = fmaxf(mx, wl[k]);
+                    }
+                    float se = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KT; ++k) {
+                        wl[k] = (k < K) ? expf(wl[k] - mx) : 0.f;
+                        se += wl[k];
+                    }
+                    const float inv_se = 1.0f / se;
+                    if (t >= 2) mbar_wait(XFREE((g - 2) % 3u), ((g - 2) / 3u) & 1u);   // the MMAs that read this R buffer have retired
+                    uint8_t* rbp = bp + o_r + (g & 1u) * 8192u;
+                    const uint32_t rbase = (uint32_t)(tid >> 6) * 4096u + (uint32_t)(tid & 7) * 2u;
+                    const int c16 = (tid & 63) >> 3;
+#pragma unroll
+                    for (int k = 0; k < KT; ++k)
+                        if (k < K) {
+                            const float r = valid ? fmaf(wl[k], inv_se, prm.alpha) * inv_den : 0.f;   // ref :380-383
+                            s0[k] += r;
+                            const float rs = r * SR;
+                            const __half h = __float2half_rn(rs);
+                            const uint32_t off = rbase + (uint32_t)k * 128u + (uint32_t)(((c16 ^ (k & 7)) & 7) << 4);
+                            *reinterpret_cast<__half*>(rbp + off) = h;                                         // row k
+                            *reinterpret_cast<__half*>(rbp + off + 2048u) = __float2half_rn(rs - __half2float(h));   // row 16 + k
+                        }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (tid == 0) MGP_PROF(g, 4);
+                    if (lane == 0) mbar_arrive(RFULL(g & 1u));
+                }
+            }
+            tile_ctr += (uint32_t)ntiles;
+            if (tid == 0) MGP_PROF(tile_ctr - 1, 6);
+            // ---- S0 over the class; the owners wait for the last statistics MMAs of this loop
+            if (warp < 4) {
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    const float v = warp_sum(s0[k]);
+                    if (lane == 0) s_red[warp * 16 + k] = v;
+                }
+                const uint32_t gl = tile_ctr - 1;
+                mbar_wait(XFREE(gl % 3u), (gl / 3u) & 1u);
+                tc_fence_after();
+            }
+            __syncthreads();
+        } else {
         for (int t = 0; t < ntiles; ++t, ++tile_ctr) {
             const uint32_t par = tile_ctr & 1u;
             if (tid == ISSUER) {
@@ -446,6 +665,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         mbar_wait(bar_s, (tile_ctr - 1) & 1u);                        // all statistics MMAs of this loop have retired
         tc_fence_after();
         __syncthreads();
+        }   // !PIPE
         if (tid < K) s_s0[tid] = (s_red[tid] + s_red[16 + tid]) + (s_red[32 + tid] + s_red[48 + tid]);
         uint32_t sacc[16], sacc1[16];
         if (own) {
@@ -492,7 +712,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
         if (tid == 0) MGP_PROF(tile_ctr - 1, 7);
     }
     if (tid == 0) MGP_PROF(63, 4);
-    replay(step0 + L * (ord + 1), L * (n_active - ord - 1));
+    replay(step0 + L * (ord + 1), L * (n_active - ord - 1), s_misc + 4);
     if (tid == 0) MGP_PROF(63, 5);
     write_back();
     if (tid < K) prm.weight[(size_t)c * P + (size_t)c * K + tid] = s_pi[tid];
@@ -506,13 +726,14 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
 }
 
 template <int D>
-size_t em_tc_smem(int kt) {
-    return 1024 + 2 * (size_t)(D / 64) * TR * 128 + (size_t)(D / 64) * 4096 + 8192 +
-           ((size_t)kt * kt + 2 * TAB + 136 + 6 * 16 + 8 + 8 * (size_t)(kt * (kt - 1) / 2)) * 4 + 64;
+size_t em_tc_smem(int kt, bool pipe) {
+    return 1024 + (pipe ? 3 : 1) * 2 * (size_t)(D / 64) * TR * 128 + (size_t)(D / 64) * 4096 + (pipe ? 2 : 1) * 8192 +
+           ((size_t)kt * kt + 2 * TAB + 136 + 6 * 16 + 8 + 8 * (size_t)(32 * ((kt * (kt - 1) / 2 + kt + 31) / 32))) * 4 + 128;
 }
 
 }  // namespace
 
+int mgp_opt_em_pipe();   // abi.cu
 static long long* g_em_tc_prof = nullptr;
 static int g_em_tc_prof_class = 0;
 void mgp_em_tc_set_prof(void* p, int cls) { g_em_tc_prof = reinterpret_cast<long long*>(p); g_em_tc_prof_class = cls; }
@@ -535,21 +756,35 @@ int mgp_em_tc_launch(const void* shadow_h, const void* shadow_l, const float* sh
     prm.alpha = alpha; prm.tau = (float)tau; prm.omtau = (float)(1.0 - tau); prm.lamda = lamda;
     prm.num_em_loop = num_em_loop; prm.C = C; prm.K = K; prm.cap = cap;
     prm.prof = g_em_tc_prof; prm.prof_class = g_em_tc_prof_class;
-#define MGP_EMTC(DD, KK)                                                                                            \
+    prm.clist = reinterpret_cast<const int32_t*>(bias_corr + (size_t)5 * num_em_loop * C + 4);
+    const bool pipe = mgp_opt_em_pipe() != 0 && D == 128;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int devi = 0;
+        MGP_CUDA(cudaGetDevice(&devi));
+        MGP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, devi));
+    }
+    prm.pipe_max = pipe ? n_sm : 0;
+#define MGP_EMTC(DD, KK, PP)                                                                                        \
     do {                                                                                                            \
-        const size_t smem = em_tc_smem<DD>(KK);                                                                     \
-        MGP_CUDA(cudaFuncSetAttribute(em_tc_kernel<DD, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        em_tc_kernel<DD, KK><<<C, 256, smem, st>>>(mh, ml, prm);                                                    \
+        const size_t smem = em_tc_smem<DD>(KK, PP);                                                                 \
+        MGP_CUDA(cudaFuncSetAttribute(em_tc_kernel<DD, KK, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        em_tc_kernel<DD, KK, PP><<<C, 256, smem, st>>>(mh, ml, prm);                                                \
+    } while (0)
+#define MGP_EMTC_K(DD, PP)                                                                                          \
+    do {                                                                                                            \
+        if (K <= 5) MGP_EMTC(DD, 5, PP);                                                                            \
+        else if (K <= 10) MGP_EMTC(DD, 10, PP);                                                                     \
+        else MGP_EMTC(DD, 16, PP);                                                                                  \
     } while (0)
     if (D == 128) {
-        if (K <= 5) MGP_EMTC(128, 5);
-        else if (K <= 10) MGP_EMTC(128, 10);
-        else MGP_EMTC(128, 16);
+        if (pipe) MGP_EMTC_K(128, true);
+        MGP_CHECK_LAUNCH();
+        MGP_EMTC_K(128, false);                      // (returns at once when the pipelined kernel took the call)
     } else {
-        if (K <= 5) MGP_EMTC(256, 5);
-        else if (K <= 10) MGP_EMTC(256, 10);
-        else MGP_EMTC(256, 16);
+        MGP_EMTC_K(256, false);
     }
+#undef MGP_EMTC_K
 #undef MGP_EMTC
     MGP_CHECK_LAUNCH();
     return MGP_OK;

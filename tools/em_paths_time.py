@@ -18,10 +18,13 @@ for D in (128, 256):
     bench.CFG["D"] = D
     net = bench.build_model(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for name, (tc, fused) in (("tc", (1, 1)), ("fused", (0, 1)), ("multilaunch", (0, 0))):
+    for name, (tc, fused, pipe) in (("tc", (1, 1, 1)), ("tc_serial", (1, 1, 0)), ("fused", (0, 1, 1)), ("multilaunch", (0, 0, 1))):
+        if D == 256 and name == "tc_serial":
+            continue
         lib.mgp_set_option(b"em_tc", tc)
         lib.mgp_set_option(b"em_fused", fused)
-        for n_act in (200, 146):
+        lib.mgp_set_option(b"em_pipe", pipe)
+        for n_act in (200, 146, 100):
             def run():
                 net.queue.updated.zero_()
                 net.queue.updated[:n_act] = 1
@@ -29,6 +32,7 @@ for D in (128, 256):
             for _ in range(3):
                 run()
             torch.cuda.synchronize()
+            torch.cuda._sleep(20_000_000)          # ~10 ms of GPU spin: the host enqueues the 20 calls behind it, so the events see GPU time only
             e0.record()
             for _ in range(20):
                 run()

@@ -96,6 +96,11 @@ int mgp_normalize_bwd(const float* g_xhat_nd, const float* xhat_nd, const float*
  * structure), mu/sigma [P,D]; `ws` is scratch of at least mgp_logprob_ws_bytes(B, HW, P, D, math)
  * bytes (the tensor-core path stages fp16 hi/lo operands there). */
 size_t mgp_logprob_ws_bytes(int B, int HW, int P, int D, int math);
+/* 1 if mgp_logprob_fwd with this layout / shape / math mode reads the fp32 patches itself (the TMEM-resident kernel,
+ * csrc/logprob_tcz.cu), so that its workspace holds prototype-side operands only: a caller whose mu / sigma are
+ * unchanged since the previous call with the same workspace may then pass MGP_MATH_TC_ISO_REUSE and skip the
+ * prototype pre-pass (with the other tensor-core kernels *_REUSE also reuses the staged patches). */
+int mgp_logprob_ws_is_prototype_only(int out_layout, int P, int D, int math);
 int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const float* sigma, float eps,
                     float eps_log, float* out, int out_layout, int B, int HW, int P, int D,
                     int math, void* ws, size_t ws_bytes, void* stream);

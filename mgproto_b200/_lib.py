@@ -26,6 +26,7 @@ SIGNATURES = {
     "mgp_normalize_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_normalize_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mgp_logprob_ws_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mgp_logprob_ws_is_prototype_only": (_i, [_i, _i, _i, _i]),
     "mgp_logprob_fwd": (_i, [_vp, _vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "mgp_head_select": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mgp_head_select_np": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -99,6 +99,17 @@ extern "C" size_t mgp_logprob_ws_bytes(int B, int HW, int P, int D, int math) {
     return simt;
 }
 
+bool mgp_logprob_tcz_supported(int P, int D);   // logprob_tcz.cu
+extern "C" int mgp_logprob_ws_is_prototype_only(int out_layout, int P, int D, int math) {
+#ifdef MGP_WITH_TC
+    return (out_layout == MGP_OUT_LOGP_NP && (math == MGP_MATH_TC_ISO || math == MGP_MATH_TC_ISO_REUSE) && mgp_opt_tc_z() &&
+            P > 0 && mgp_logprob_tcz_supported(P, D)) ? 1 : 0;
+#else
+    (void)out_layout; (void)P; (void)D; (void)math;
+    return 0;
+#endif
+}
+
 extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const float* sigma, float eps, float eps_log,
                                float* out, int out_layout, int B, int HW, int P, int D, int math, void* ws,
                                size_t ws_bytes, void* stream) {

@@ -49,6 +49,9 @@ struct ZParams {
     int N, P, D;
     int n_xtiles, n_ptiles;
     int team;                      // CTAs per team: they share an x tile and take prototype tiles k, k + team, ...
+    int balanced;                  // 1: team = 1 and CTA i owns the pairs [i U / G, (i+1) U / G) of the x-major list of the
+                                   //    U = x tiles * prototype tiles (x tile, prototype tile) pairs -- every CTA gets U / G
+                                   //    pairs +- 1 however the x tiles divide by the grid (a CTA may start / end mid-row)
     int stages;                    // prototype ring depth
     int debug;                     // ablation (MGP_TC_DEBUG): 1 no global stores, 4 no MMAs, 8 no operand conversion, 16 no prototype loads
 };
@@ -129,7 +132,19 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int TS = prm.team;
     const int n_teams = gridDim.x / TS, team = blockIdx.x / TS, k0 = blockIdx.x % TS;
     const int n_ptiles = prm.n_ptiles, n_xtiles = prm.n_xtiles;
-    const bool has_work = (team < n_teams) && (k0 < n_ptiles);
+    // schedule: this CTA visits n_my_x x tiles xt_of(c), c = 0.., and for each the prototype tiles
+    // p_begin(c), p_begin(c) + p_step, ... < p_end(c)
+    const bool bal = prm.balanced != 0;
+    const long long n_pairs = (long long)n_xtiles * n_ptiles;
+    const long long u0 = n_pairs * blockIdx.x / gridDim.x, u1 = n_pairs * (blockIdx.x + 1) / gridDim.x;
+    const int xt_first = (int)(u0 / n_ptiles), xt_last = (int)((u1 - 1) / n_ptiles);
+    const int n_my_x = bal ? (u1 > u0 ? xt_last - xt_first + 1 : 0)
+                           : ((team < n_teams && k0 < n_ptiles && team < n_xtiles) ? (n_xtiles - team + n_teams - 1) / n_teams : 0);
+    const int p_step = bal ? 1 : TS;
+    auto xt_of = [&](int c) { return bal ? xt_first + c : team + c * n_teams; };
+    auto p_begin = [&](int c) { return bal ? (c == 0 ? (int)(u0 - (long long)xt_first * n_ptiles) : 0) : k0; };
+    auto p_end = [&](int c) { return (bal && xt_first + c == xt_last) ? (int)(u1 - (long long)xt_last * n_ptiles) : n_ptiles; };
+    const bool has_work = n_my_x > 0;
     const uint32_t idesc = umma_idesc_f16(XT, PT);
     // The kernel is launched with programmatic stream serialisation behind the prototype pre-pass: everything up to
     // here, the first patch tile's TMA load and its conversion overlap that pre-pass; whoever READS its outputs
@@ -139,8 +154,8 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         // nothing to do (tiny problems)
     } else if (warp == 2 && lane == 0) {
         // =========================== x-tile TMA producer (fp32 rows, 128B-swizzled 32-float blocks) ===============
-        int c = 0;
-        for (int xt = team; xt < n_xtiles; xt += n_teams, ++c) {
+        for (int c = 0; c < n_my_x; ++c) {
+            const int xt = xt_of(c);
             if (c > 0) mbar_wait(XEMPTY, (uint32_t)((c - 1) & 1));           // the converters have read the previous tile
             mbar_expect_tx(XFULL, X_BYTES);
 #pragma unroll
@@ -151,8 +166,8 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         asm volatile("griddepcontrol.wait;" ::: "memory");
         int stage = 0;
         uint32_t phase = 0;
-        for (int xt = team; xt < n_xtiles; xt += n_teams)
-            for (int pt = k0; pt < n_ptiles; pt += TS)
+        for (int c = 0; c < n_my_x; ++c)
+            for (int pt = p_begin(c); pt < p_end(c); pt += p_step)
                 for (int kb = 0; kb < NKB; ++kb) {
                     mbar_wait(EMPTY(stage), phase ^ 1u);
                     if (prm.debug & 16) {
@@ -167,14 +182,14 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 }
     } else if (warp == 1 && lane == 0) {
         // =========================== MMA issuer (A = patch tile in TMEM, B = prototype block in smem) ===============
-        int stage = 0, acc = 0, c = 0;
+        int stage = 0, acc = 0;
         uint32_t phase = 0, acc_par = 0;
-        for (int xt = team; xt < n_xtiles; xt += n_teams, ++c) {
+        for (int c = 0; c < n_my_x; ++c) {
             const int ab = c & 1;
             mbar_wait(AFULL(ab), (uint32_t)((c >> 1) & 1));
             tc_fence_after();
             const uint32_t a_hi = t_a + (uint32_t)ab * ACOLS, a_lo = a_hi + D / 2;
-            for (int pt = k0; pt < n_ptiles; pt += TS) {
+            for (int pt = p_begin(c); pt < p_end(c); pt += p_step) {
                 mbar_wait(TEMPTY(acc), acc_par ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = t_acc + (uint32_t)(acc * 128);
@@ -260,7 +275,7 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 mbar_arrive(AFULL(ab));                                                   // operand (this warp's share) in TMEM
             }
         };
-        int acc = 0, c = 0;
+        int acc = 0;
         uint32_t acc_par = 0;
         convert(0);
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -273,19 +288,19 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             s_e[ti * 384 + 128 + (i & 127)] = ok ? prm.e1[p] : 0.f;
             s_e[ti * 384 + 256 + (i & 127)] = ok ? prm.e2[p] : 0.f;
         }
-        for (int xt = team; xt < n_xtiles; xt += n_teams, ++c) {
+        for (int c = 0; c < n_my_x; ++c) {
             const int ab = c & 1;
-            const int row0 = xt * XT;
+            const int row0 = xt_of(c) * XT;
             asm volatile("bar.sync 1, 256;" ::: "memory");                                // s_sn[ab] complete / visible
             const float sn = s_sn[ab * 128 + row];
             const int n = row0 + row;
-            const int n_my = (n_ptiles - k0 + TS - 1) / TS;
+            const int n_my = (p_end(c) - p_begin(c) + p_step - 1) / p_step;
             int ti = 0;
-            for (int pt = k0; pt < n_ptiles; pt += TS, ++ti) {
+            for (int pt = p_begin(c); pt < p_end(c); pt += p_step, ++ti) {
                 // the next x tile's operand is converted half-way through this tile's prototype tiles: the first
                 // accumulators are drained first (the MMA warp is never held up), and the operand is ready well before
                 // the last prototype tile of this x tile has been issued
-                if (ti == n_my / 2 && xt + n_teams < n_xtiles) convert(c + 1);
+                if (ti == n_my / 2 && c + 1 < n_my_x) convert(c + 1);
                 // the two warp groups drain alternate accumulators (tiles): each has two MMA tile times per tile
                 if (acc != h) { acc ^= 1; continue; }
                 mbar_wait(TFULL(acc), acc_par);
@@ -431,12 +446,17 @@ int mgp_logprob_tcz_launch(const float* xhat, const void* bh, const void* bl, co
     n_teams = sms / team;
     if (n_teams > prm.n_xtiles) n_teams = prm.n_xtiles;
     if (n_teams < 1) return MGP_ERR_UNSUPPORTED;
+    // balanced pair schedule whenever one CTA can cache every prototype tile's constants (MGP_TC_TEAM forces the team schedule)
+    const bool balanced = !(ts && atoi(ts) > 0) && prm.n_ptiles <= MAXT;
+    if (balanced) team = 1;
     prm.team = team;
+    prm.balanced = balanced ? 1 : 0;
     int stages = (int)((227 * 1024 - 1024 - 4096 - MAXT * 1536 - 8 * 4096 - x_bytes) / (2 * PSUB));
     if (stages > 8) stages = 8;
     if (stages < 2) return MGP_ERR_UNSUPPORTED;
     prm.stages = stages;
-    const int grid = n_teams * team;
+    const long long n_pairs = (long long)prm.n_xtiles * prm.n_ptiles;
+    const int grid = balanced ? (int)(n_pairs < sms ? n_pairs : sms) : n_teams * team;
     const size_t smem = 1024 + x_bytes + (size_t)stages * 2 * PSUB + 8 * 4096 + MAXT * 1536 + 4096;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

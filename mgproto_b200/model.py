@@ -344,6 +344,7 @@ class MGProto(nn.Module):
                            order, sched, stats, n_split, L, self.alpha, lr, b1, b2, eps, self.tau, shadow=shadow,
                            sigma_iso=iso, status=self._em_status)
             self._em_dirty = True
+            self._bump_versions()
             return
         ops.em_plan(q.updated, q.mem_len, order, sched, 0, cap, L, adam_step=self._adam_step_dev)
         ops.em_update(None, n_split, cap, order, sched, mu, sg, wt, st["exp_avg"], st["exp_avg_sq"], 0, L, 0,
@@ -361,6 +362,13 @@ class MGProto(nn.Module):
         ops.em_update(None, n_split, cap, order, sched, mu, sg, wt, st["exp_avg"], st["exp_avg_sq"], 0, L, 2,
                       lr, b1, b2, eps, self.tau)
         self._em_dirty = True
+        self._bump_versions()
+
+    def _bump_versions(self):
+        """The EM kernels write the means and the mixture weights through raw pointers: tell torch (autograd's
+        saved-tensor checks, and the caches keyed on the version counter such as ops.logprob's prototype operands)."""
+        torch.autograd.graph.increment_version(self.prototype_means)
+        torch.autograd.graph.increment_version(self.last_layer.weight)
 
     def _update_GMM_generic(self, order, sched, stats, n_split, r0, r1, world):
         """Any other optimiser: same order of operations as the reference, one optimiser.step()

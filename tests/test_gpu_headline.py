@@ -222,7 +222,9 @@ def _run_em(g, math, path):
         for it in range(2):
             net.queue.updated |= _t(flags[it], torch.uint8)
             np.testing.assert_array_equal(net.memory_updated_cls.numpy(), g["flags%d" % it])
+            v0 = net.prototype_means._version
             net.update_GMM()
+            assert net.prototype_means._version > v0                  # raw-pointer writes are announced to torch
             assert int(net.memory_updated_cls.sum()) == 0
             w = net.last_layer.weight.detach().cpu().numpy()
             outs.append((net.prototype_means.detach().cpu().numpy().copy(),

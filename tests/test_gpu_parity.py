@@ -365,6 +365,39 @@ def test_logprob_tmem_resident_kernel_vs_fp64(shape):
     torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5)
 
 
+def test_logprob_prototype_operands_are_cached_until_the_prototypes_change():
+    """ops.logprob (auto, isotropic sigma, [N,P]) keeps the prototype-side operands of the TMEM-resident kernel while
+    mu / sigma are unchanged (version counter) and rebuilds them after an in-place change -- including update_GMM's
+    raw-pointer writes, which bump the counters explicitly."""
+    from mgproto_b200 import ops, _lib
+    if not _lib.load().mgp_has_tensor_core_path():
+        pytest.skip("library built without the tcgen05 path")
+    B, HW, P, D = 4, 49, 300, 128
+    g = torch.Generator().manual_seed(5)
+    x = F.normalize(torch.randn(B * HW, D, generator=g), dim=1).to(_dev())
+    mu = F.normalize(torch.rand(P, D, generator=g), dim=1).to(_dev())
+    sg = torch.full((P, D), 0.4, device=_dev())
+
+    def ref(m):
+        return (-0.5 * D * np.log(2 * np.pi) - sg.double().log().sum(1)[None, :]
+                - 0.5 * (((x.double()[:, None, :] - m.double()[None]) / sg.double()[None]) ** 2).sum(-1))
+    ops._PROTO_OPERANDS.clear()
+    n0 = ops.launch_count()
+    a = ops.logprob(x, mu, sg, 0, math="auto")
+    n1 = ops.launch_count()
+    b = ops.logprob(x, mu, sg, 0, math="auto")                         # hit: the pre-pass is skipped
+    n2 = ops.launch_count()
+    assert len(ops._PROTO_OPERANDS) == 1 and (n2 - n1) < (n1 - n0)
+    assert torch.equal(a, b)
+    torch.testing.assert_close(a.double(), ref(mu), rtol=2e-5, atol=2e-5)
+    mu.mul_(0.5)                                                       # in place: new version, stale operands must not be used
+    c = ops.logprob(x, mu, sg, 0, math="auto")
+    torch.testing.assert_close(c.double(), ref(mu), rtol=2e-5, atol=2e-5)
+    v = mu._version
+    torch.autograd.graph.increment_version(mu)                         # what MGProto.update_GMM does after its kernels
+    assert mu._version == v + 1
+
+
 def test_logprob_tc_baseline_size_properties():
     """cfg2 size (B=256, P=2000, D=128): KA1 identity on a strided sample + exact agreement of the
     three output layouts with each other (size-independent properties; no CPU oracle at this size)."""

@@ -100,8 +100,7 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     auto TFULL = [&](int i) { return bar0 + 8u * (22 + i); };
     auto TEMPTY = [&](int i) { return bar0 + 8u * (24 + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
-    float* s_snp = reinterpret_cast<float*>(bars + 28);        // [2][128] partial |x|^2 of the two column halves
-    float* s_sn = s_snp + 256;                                 // [2][128] |x|^2 per A buffer
+    float* s_snp = reinterpret_cast<float*>(bars + 28);        // [2 A buffers][2 column halves][128] partial |x|^2
     float* s_e = reinterpret_cast<float*>(bp + o_cst);         // loaded once: a CTA revisits the same <= MAXT tiles for every x tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,11 +263,9 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                       "r"(lo[13]), "r"(lo[14]), "r"(lo[15])
                     : "memory");
             }
-            s_snp[h * 128 + row] = ss;
+            s_snp[(ab * 2 + h) * 128 + row] = ss;                                        // (summed by the reader after the tile's barrier)
             tmem_st_wait();
             tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");                                // both halves' partial norms are in
-            if (h == 0) s_sn[ab * 128 + row] = s_snp[row] + s_snp[128 + row];
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(XEMPTY);                                                      // landing tile consumed
@@ -291,8 +288,8 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         for (int c = 0; c < n_my_x; ++c) {
             const int ab = c & 1;
             const int row0 = xt_of(c) * XT;
-            asm volatile("bar.sync 1, 256;" ::: "memory");                                // s_sn[ab] complete / visible
-            const float sn = s_sn[ab * 128 + row];
+            asm volatile("bar.sync 1, 256;" ::: "memory");                                // both halves' |x|^2 of this tile are in
+            const float sn = s_snp[(ab * 2) * 128 + row] + s_snp[(ab * 2 + 1) * 128 + row];
             const int n = row0 + row;
             const int n_my = (p_end(c) - p_begin(c) + p_step - 1) / p_step;
             int ti = 0;
@@ -300,7 +297,8 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 // the next x tile's operand is converted half-way through this tile's prototype tiles: the first
                 // accumulators are drained first (the MMA warp is never held up), and the operand is ready well before
                 // the last prototype tile of this x tile has been issued
-                if (ti == n_my / 2 && c + 1 < n_my_x) convert(c + 1);
+                // (the two warp groups convert one tile apart, so that one of them keeps draining / storing)
+                if (ti == min(n_my / 2 + h, n_my - 1) && c + 1 < n_my_x) convert(c + 1);
                 // the two warp groups drain alternate accumulators (tiles): each has two MMA tile times per tile
                 if (acc != h) { acc ^= 1; continue; }
                 mbar_wait(TFULL(acc), acc_par);

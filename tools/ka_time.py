@@ -42,7 +42,7 @@ for z in (1, 0):
     lib.mgp_set_option(b"tc_z", z)
     for team in (["0", "4", "1"] if z else ["4"]):
         os.environ["MGP_TC_TEAM"] = team
-        for dbg in (["0", "1", "4"] if (z and team == "0") else ["0"]):
+        for dbg in (os.environ.get("KA_DEBUGS", "0,1,4").split(",") if (z and team == "0") else ["0"]):
             os.environ["MGP_TC_DEBUG"] = dbg
             run("z=%d team=%s debug=%s" % (z, team, dbg))
 os.environ["MGP_TC_DEBUG"] = "0"

@@ -433,17 +433,56 @@ __global__ void proto_weight_kernel(const float* __restrict__ mu, const float* _
 
 constexpr int LCAP = 2304;   // entries per drain (>= P + K(T-1) of the labelled cfg: one drain per image)
 
-// grid (B, D/DC), DC = 64: CTA (b, j) produces dims [64j, 64j+64) of image b's rows of g_xhat (zeroed by the
-// caller).  Entries with gradient are compacted in a fixed order, stably counting-sorted by patch row, then each
+// grid (B, D/DC), DC = 32 VEC (VEC = 4 floats per lane when D is a multiple of 128: ONE CTA per image at D = 128, so the
+// list is built and sorted once; VEC = 2 otherwise): CTA (b, j) produces dims [DC j, DC j + DC) of image b's rows of
+// g_xhat (zeroed by the caller).  Entries with gradient are compacted in a fixed order, stably counting-sorted by patch row, then each
 // warp walks one eighth of the sorted list with lanes owning two dims each (see the walk below) and adds every
 // finished row straight into global memory (a row has exactly one writer per drain): balanced however the mined
 // patches cluster, no atomics, fixed summation order, 48 KB of shared memory -> 4 CTAs per SM.
-__global__ void __launch_bounds__(256, 4)
+template <int VEC> struct LaneVec { float v[VEC]; };
+template <int VEC>
+__device__ __forceinline__ LaneVec<VEC> lv_ldg(const float* p) {
+    LaneVec<VEC> r;
+    if constexpr (VEC == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); r.v[0] = t.x; r.v[1] = t.y; }
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ LaneVec<VEC> lv_ldcg(const float* p) {
+    LaneVec<VEC> r;
+    if constexpr (VEC == 4) { const float4 t = __ldcg(reinterpret_cast<const float4*>(p)); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else { const float2 t = __ldcg(reinterpret_cast<const float2*>(p)); r.v[0] = t.x; r.v[1] = t.y; }
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ LaneVec<VEC> lv_ld(const float* p) {
+    LaneVec<VEC> r;
+    if constexpr (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else { const float2 t = *reinterpret_cast<const float2*>(p); r.v[0] = t.x; r.v[1] = t.y; }
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ void lv_st(float* p, const LaneVec<VEC>& r) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    else *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+}
+template <int VEC>
+__device__ __forceinline__ LaneVec<VEC> lv_zero() {
+    LaneVec<VEC> r;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = 0.f;
+    return r;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256, VEC == 4 ? 2 : 4)
 head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, const float* __restrict__ vals,
                 const int32_t* __restrict__ idx, const float* __restrict__ weight, const int64_t* __restrict__ gt,
                 const float* __restrict__ xhat, const float* __restrict__ w, const float* __restrict__ wm,
                 const float* __restrict__ wsc, const int* __restrict__ noniso, float* __restrict__ g_xhat, int HW,
-                int C, int K, int D, int T, int DC) {
+                int C, int K, int D, int T) {
+    constexpr int DC = 32 * VEC;
+    using LV = LaneVec<VEC>;
     extern __shared__ float smem[];
     const bool aniso = (*noniso != 0);
     unsigned* lkey = reinterpret_cast<unsigned*>(smem);     // [LCAP] p*1024 + n
@@ -455,7 +494,7 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
     float* qg = Qs + C;                                     // [T]  gl/exp(logit) of the GT class
     __shared__ int wcount[8];
     __shared__ int lcount;
-    __shared__ __align__(8) float part[16 * 64];            // boundary runs of the warps' list ranges (s1 vectors)
+    __shared__ __align__(16) float part[16 * DC];           // boundary runs of the warps' list ranges (s1 vectors)
     __shared__ float part2[16];                             // ... their scalar sum_e a_e w_p (isotropic sigma)
     __shared__ int prow[16];
     __shared__ int mrow[16], mcount;                        // boundary runs merged by row
@@ -629,7 +668,7 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
             // `part`, merged by row in a fixed order and added afterwards -> no atomics, deterministic.
             if (threadIdx.x < 16) prow[threadIdx.x] = -1;
             __syncthreads();
-            const int dl = 2 * lane;
+            const int dl = VEC * lane;
             const bool dok2 = dl < dc;
             const int dle = dok2 ? dl : 0;                       // lanes beyond dc shadow the first dims, never store
             const float* xcol2 = xhat + (size_t)b * HW * D + d0 + dle;
@@ -640,19 +679,21 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                 const float* wcol_l = w + d0 + dle;
                 int cur_n = -1;
                 bool first_run = true;
-                float2 s1 = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
-                float2 xpre = make_float2(0.f, 0.f), gpre = make_float2(0.f, 0.f);
+                LV s1 = lv_zero<VEC>(), s2v = lv_zero<VEC>(), xpre = lv_zero<VEC>(), gpre = lv_zero<VEC>();
                 float s2 = 0.f;
                 auto flush = [&](int slot) {
                     if (slot < 0) {
-                        float2 v = gpre;
-                        v.x += aniso ? fmaf(-xpre.x, s2v.x, s1.x) : fmaf(-xpre.x, s2, s1.x);
-                        v.y += aniso ? fmaf(-xpre.y, s2v.y, s1.y) : fmaf(-xpre.y, s2, s1.y);
-                        if (dok2) *reinterpret_cast<float2*>(gcol + (size_t)cur_n * D) = v;
+                        LV v = gpre;
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) v.v[i] += aniso ? fmaf(-xpre.v[i], s2v.v[i], s1.v[i]) : fmaf(-xpre.v[i], s2, s1.v[i]);
+                        if (dok2) lv_st<VEC>(gcol + (size_t)cur_n * D, v);
                     } else {
-                        float2 v = s1;                            // isotropic: raw sums, xhat applied after the merge
-                        if (aniso) { v.x = fmaf(-xpre.x, s2v.x, v.x); v.y = fmaf(-xpre.y, s2v.y, v.y); }
-                        if (dok2) *reinterpret_cast<float2*>(part + (warp * 2 + slot) * 64 + dl) = v;
+                        LV v = s1;                                // isotropic: raw sums, xhat applied after the merge
+                        if (aniso) {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) v.v[i] = fmaf(-xpre.v[i], s2v.v[i], v.v[i]);
+                        }
+                        if (dok2) lv_st<VEC>(part + (warp * 2 + slot) * DC + dl, v);
                         if (lane == 0) { part2[warp * 2 + slot] = aniso ? 0.f : s2; prow[warp * 2 + slot] = cur_n; }
                     }
                 };
@@ -666,13 +707,13 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                         const float v2 = (!AN && ok) ? av * __ldg(wsc + (kk >> 10)) : 0.f;
                         const int m = min(32, we - i0);
                         for (int j0 = 0; j0 < m; j0 += 8) {
-                            float2 fm[8], fw[8];
+                            LV fm[8], fw[8];
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
                                 const unsigned ku = __shfl_sync(0xffffffffu, kk, j0 + u);
                                 const unsigned po = (ku >> 10) * (unsigned)D;
-                                fm[u] = __ldg(reinterpret_cast<const float2*>(wmcol_l + po));
-                                if (AN) fw[u] = __ldg(reinterpret_cast<const float2*>(wcol_l + po));
+                                fm[u] = lv_ldg<VEC>(wmcol_l + po);
+                                if (AN) fw[u] = lv_ldg<VEC>(wcol_l + po);
                             }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
@@ -684,17 +725,17 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                                         first_run = false;
                                     }
                                     cur_n = n;
-                                    xpre = __ldg(reinterpret_cast<const float2*>(xcol2 + (size_t)n * D));
-                                    gpre = __ldcg(reinterpret_cast<const float2*>(gcol + (size_t)n * D));
-                                    s1 = make_float2(0.f, 0.f);
-                                    s2v = make_float2(0.f, 0.f);
+                                    xpre = lv_ldg<VEC>(xcol2 + (size_t)n * D);
+                                    gpre = lv_ldcg<VEC>(gcol + (size_t)n * D);
+                                    s1 = lv_zero<VEC>();
+                                    s2v = lv_zero<VEC>();
                                     s2 = 0.f;
                                 }
-                                s1.x = fmaf(a, fm[u].x, s1.x);
-                                s1.y = fmaf(a, fm[u].y, s1.y);
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) s1.v[i] = fmaf(a, fm[u].v[i], s1.v[i]);
                                 if (AN) {
-                                    s2v.x = fmaf(a, fw[u].x, s2v.x);
-                                    s2v.y = fmaf(a, fw[u].y, s2v.y);
+#pragma unroll
+                                    for (int i = 0; i < VEC; ++i) s2v.v[i] = fmaf(a, fw[u].v[i], s2v.v[i]);
                                 } else {
                                     s2 += __shfl_sync(0xffffffffu, v2, j0 + u);
                                 }
@@ -708,17 +749,19 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
             __syncthreads();
             if (warp == 0) {                                      // merge the parked runs by row, in list order (in place)
                 int j = -1, last = -1;
-                float2 acc = make_float2(0.f, 0.f);
+                LV acc = lv_zero<VEC>();
                 float a2 = 0.f;
                 for (int i = 0; i < 16; ++i) {
                     const int n = prow[i];
                     if (n < 0) continue;
-                    const float2 v = *reinterpret_cast<const float2*>(part + i * 64 + dl);
+                    const LV v = lv_ld<VEC>(part + i * DC + dl);
                     const float p2 = part2[i];
                     __syncwarp();
-                    if (n != last) { ++j; last = n; acc = make_float2(0.f, 0.f); a2 = 0.f; }
-                    acc.x += v.x; acc.y += v.y; a2 += p2;
-                    *reinterpret_cast<float2*>(part + j * 64 + dl) = acc;
+                    if (n != last) { ++j; last = n; acc = lv_zero<VEC>(); a2 = 0.f; }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc.v[q] += v.v[q];
+                    a2 += p2;
+                    lv_st<VEC>(part + j * DC + dl, acc);
                     if (lane == 0) { part2[j] = a2; mrow[j] = n; }
                     __syncwarp();
                 }
@@ -727,13 +770,13 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
             __syncthreads();
             for (int j = warp; j < mcount; j += 8) {
                 const int n = mrow[j];
-                const float2 xv = __ldg(reinterpret_cast<const float2*>(xcol2 + (size_t)n * D));
-                float2 gv = __ldcg(reinterpret_cast<const float2*>(gcol + (size_t)n * D));
-                const float2 v = *reinterpret_cast<const float2*>(part + j * 64 + dl);
+                const LV xv = lv_ldg<VEC>(xcol2 + (size_t)n * D);
+                LV gv = lv_ldcg<VEC>(gcol + (size_t)n * D);
+                const LV v = lv_ld<VEC>(part + j * DC + dl);
                 const float p2 = part2[j];
-                gv.x += fmaf(-xv.x, p2, v.x);
-                gv.y += fmaf(-xv.y, p2, v.y);
-                if (dok2) *reinterpret_cast<float2*>(gcol + (size_t)n * D) = gv;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) gv.v[q] += fmaf(-xv.v[q], p2, v.v[q]);
+                if (dok2) lv_st<VEC>(gcol + (size_t)n * D, gv);
             }
             __syncthreads();
             if (threadIdx.x == 0) lcount = 0;
@@ -978,14 +1021,21 @@ extern "C" int mgp_head_bwd(const float* grad_logits, const float* logits, const
     MGP_CUDA(cudaMemsetAsync(noniso, 0, sizeof(int), st));
     proto_weight_kernel<<<(unsigned)((npd + 255) / 256), 256, 0, st>>>(mu, sigma, w, wm, wsc, noniso, npd, D);
     MGP_CHECK_LAUNCH();
-    const int DC = 64;                                       // D-chunk per CTA: 8 warps x 8 dims
+    // dims per CTA: 32 lanes x 4 (one CTA per image at D = 128: the entry list is built and sorted once) or x 2
+    static const bool vec2_forced = getenv("MGP_HEAD_BWD_VEC2") != nullptr;
+    const int DC = ((D % 128) == 0 && !vec2_forced) ? 128 : 64;
     size_t smem = (size_t)LCAP * 16 + (size_t)(8 * HW + C + T) * 4;
-    if (smem > 220 * 1024) return MGP_ERR_UNSUPPORTED;
-    MGP_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 200 * 1024) return MGP_ERR_UNSUPPORTED;
+    MGP_CUDA(cudaFuncSetAttribute(head_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGP_CUDA(cudaFuncSetAttribute(head_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MGP_CUDA(cudaMemsetAsync(g_xhat, 0, (size_t)B * HW * D * sizeof(float), st));   // rows without mined patches stay zero
     dim3 grid(B, (D + DC - 1) / DC);
-    head_bwd_kernel<<<grid, 256, smem, st>>>(grad_logits, logits, vals, idx, weight_cp, gt, xhat_nd, w, wm, wsc, noniso,
-                                             g_xhat, HW, C, K, D, T, DC);
+    if (DC == 128)
+        head_bwd_kernel<4><<<grid, 256, smem, st>>>(grad_logits, logits, vals, idx, weight_cp, gt, xhat_nd, w, wm, wsc, noniso,
+                                                    g_xhat, HW, C, K, D, T);
+    else
+        head_bwd_kernel<2><<<grid, 256, smem, st>>>(grad_logits, logits, vals, idx, weight_cp, gt, xhat_nd, w, wm, wsc, noniso,
+                                                    g_xhat, HW, C, K, D, T);
     MGP_CHECK_LAUNCH();
     return mgp_normalize_bwd(g_xhat, xhat_nd, inv_norm, g_x_nchw, B, D, HW, stream);
 }

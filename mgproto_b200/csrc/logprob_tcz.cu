@@ -77,9 +77,12 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                  const ZParams prm) {
     constexpr int NKB = D / KB;                    // prototype K blocks per tile
     constexpr int NXB = D / 32;                    // fp32 landing blocks of [128 rows x 32 floats] (128 B rows, swizzled)
+    constexpr int XLB = NXB < 4 ? NXB : 4;         // ... of which the landing buffer holds at most 4 (64 KiB):
+    constexpr int NPH = NXB / XLB;                 //     a D = 256 patch tile lands and is converted in two phases
     constexpr uint32_t XB_BYTES = XT * 128;        // 16 KiB
-    constexpr uint32_t X_BYTES = NXB * XB_BYTES;   // fp32 patch tile
+    constexpr uint32_t X_BYTES = XLB * XB_BYTES;   // fp32 landing buffer
     constexpr int ACOLS = D;                       // TMEM columns of one A buffer: D/2 (hi) + D/2 (lo)
+    constexpr int NAB = (D <= 128) ? 2 : 1;        // A buffers in tensor memory: 2 x 128 accumulator columns + NAB x ACOLS <= 512
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -153,12 +156,16 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         // nothing to do (tiny problems)
     } else if (warp == 2 && lane == 0) {
         // =========================== x-tile TMA producer (fp32 rows, 128B-swizzled 32-float blocks) ===============
+        int l = 0;                                                           // landing-buffer fills so far
         for (int c = 0; c < n_my_x; ++c) {
             const int xt = xt_of(c);
-            if (c > 0) mbar_wait(XEMPTY, (uint32_t)((c - 1) & 1));           // the converters have read the previous tile
-            mbar_expect_tx(XFULL, X_BYTES);
+            for (int ph = 0; ph < NPH; ++ph, ++l) {
+                if (l > 0) mbar_wait(XEMPTY, (uint32_t)((l - 1) & 1));       // the converters have read the previous fill
+                mbar_expect_tx(XFULL, X_BYTES);
 #pragma unroll
-            for (int b = 0; b < NXB; ++b) tma_load_2d(base + o_x + b * XB_BYTES, &map_x, b * 32, xt * XT, XFULL);
+                for (int b = 0; b < XLB; ++b)
+                    tma_load_2d(base + o_x + b * XB_BYTES, &map_x, (ph * XLB + b) * 32, xt * XT, XFULL);
+            }
         }
     } else if (warp == 0 && lane == 0) {
         // =========================== prototype TMA producer ===========================
@@ -184,8 +191,8 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_par = 0;
         for (int c = 0; c < n_my_x; ++c) {
-            const int ab = c & 1;
-            mbar_wait(AFULL(ab), (uint32_t)((c >> 1) & 1));
+            const int ab = c % NAB;
+            mbar_wait(AFULL(ab), (uint32_t)((c / NAB) & 1));
             tc_fence_after();
             const uint32_t a_hi = t_a + (uint32_t)ab * ACOLS, a_lo = a_hi + D / 2;
             for (int pt = p_begin(c); pt < p_end(c); pt += p_step) {
@@ -221,14 +228,16 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         // fp32 landing tile -> fp16 hi / lo of 256 x in TMEM (A buffer `ab`), |x|^2 -> s_sn[ab]
         auto convert = [&](int cc) {
-            const int ab = cc & 1;
-            mbar_wait(XFULL, (uint32_t)(cc & 1));
-            if (cc >= 2) {
-                mbar_wait(AEMPTY(ab), (uint32_t)(((cc >> 1) - 1) & 1));                   // MMAs of tile cc-2 are done with it
+            const int ab = cc % NAB;
+            float ss = 0.f;
+            constexpr int HB = XLB / 2;                                                   // landing blocks of this group per fill
+#pragma unroll 1
+            for (int ph = 0; ph < NPH; ++ph) {
+            mbar_wait(XFULL, (uint32_t)((cc * NPH + ph) & 1));
+            if (ph == 0 && cc >= NAB) {
+                mbar_wait(AEMPTY(ab), (uint32_t)(((cc / NAB) - 1) & 1));                  // the MMAs that read this buffer are done
                 tc_fence_after();
             }
-            float ss = 0.f;
-            constexpr int HB = NXB / 2;                                                   // landing blocks of this column half
 #pragma unroll
             for (int bb = 0; bb < ((prm.debug & 8) ? 0 : HB); ++bb) {
                 const uint8_t* blk = bp + o_x + (uint32_t)(h * HB + bb) * XB_BYTES + (uint32_t)row * 128u;
@@ -249,7 +258,7 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     lo[2 * j] = pack_h2(ll[0], ll[1]); lo[2 * j + 1] = pack_h2(ll[2], ll[3]);
                 }
                 // 32 elements = 16 TMEM columns per landing block; element k of the row -> column k / 2
-                const uint32_t col = (uint32_t)((h * HB + bb) * 16);
+                const uint32_t col = (uint32_t)((ph * XLB + h * HB + bb) * 16);
                 asm volatile(
                     "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                     ::"r"(t_a + (uint32_t)ab * ACOLS + col + lane_off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]),
@@ -262,6 +271,11 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                       "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(lo[8]), "r"(lo[9]), "r"(lo[10]), "r"(lo[11]), "r"(lo[12]),
                       "r"(lo[13]), "r"(lo[14]), "r"(lo[15])
                     : "memory");
+            }
+            if (ph + 1 < NPH) {                                                          // landing buffer consumed: next fill may start
+                __syncwarp();
+                if (lane == 0) mbar_arrive(XEMPTY);
+            }
             }
             s_snp[(ab * 2 + h) * 128 + row] = ss;                                        // (summed by the reader after the tile's barrier)
             tmem_st_wait();
@@ -286,7 +300,7 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             s_e[ti * 384 + 256 + (i & 127)] = ok ? prm.e2[p] : 0.f;
         }
         for (int c = 0; c < n_my_x; ++c) {
-            const int ab = c & 1;
+            const int ab = c % NAB;
             const int row0 = xt_of(c) * XT;
             asm volatile("bar.sync 1, 256;" ::: "memory");                                // both halves' |x|^2 of this tile are in
             const float sn = s_snp[(ab * 2) * 128 + row] + s_snp[(ab * 2 + 1) * 128 + row];
@@ -298,7 +312,7 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 // accumulators are drained first (the MMA warp is never held up), and the operand is ready well before
                 // the last prototype tile of this x tile has been issued
                 // (the two warp groups convert one tile apart, so that one of them keeps draining / storing)
-                if (ti == min(n_my / 2 + h, n_my - 1) && c + 1 < n_my_x) convert(c + 1);
+                if (NAB == 2 && ti == min(n_my / 2 + h, n_my - 1) && c + 1 < n_my_x) convert(c + 1);
                 // the two warp groups drain alternate accumulators (tiles): each has two MMA tile times per tile
                 if (acc != h) { acc ^= 1; continue; }
                 mbar_wait(TFULL(acc), acc_par);
@@ -357,6 +371,8 @@ logprob_z_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 acc ^= 1;
                 acc_par ^= 1u;                                                            // my accumulator comes round every other tile
             }
+            // one A buffer (D = 256): the next tile's operand can only be written once this tile's MMAs have retired
+            if (NAB == 1 && c + 1 < n_my_x) convert(c + 1);
         }
     }
     if (warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my TMA stores have landed
@@ -396,7 +412,7 @@ bool make_map_out(CUtensorMap* m, const void* ptr, uint64_t N, uint64_t P) {
 
 }  // namespace
 
-bool mgp_logprob_tcz_supported(int P, int D) { return (D == 64 || D == 128) && P >= 1 && get_encode() != nullptr; }
+bool mgp_logprob_tcz_supported(int P, int D) { return (D == 64 || D == 128 || D == 256) && P >= 1 && get_encode() != nullptr; }
 
 // bh / bl [P, 2D] fp16, e0 / e1 / e2 [P], noniso: the prototype-side workspace of logprob_tc.cu (tc_proto_prep_kernel)
 int mgp_logprob_tcz_launch(const float* xhat, const void* bh, const void* bl, const float* e0, const float* e1,
@@ -439,7 +455,7 @@ int mgp_logprob_tcz_launch(const float* xhat, const void* bh, const void* bl, co
     if (team > sms) team = sms;
     int n_teams = sms / team;
     if (n_teams > prm.n_xtiles) n_teams = prm.n_xtiles;
-    const size_t x_bytes = (size_t)XT * D * 4;
+    const size_t x_bytes = (size_t)XT * (D < 128 ? D : 128) * 4;       // landing buffer: at most 4 blocks of 32 floats
     while ((prm.n_ptiles + team - 1) / team > MAXT) ++team;              // every CTA caches its tiles' epilogue constants
     n_teams = sms / team;
     if (n_teams > prm.n_xtiles) n_teams = prm.n_xtiles;
@@ -466,7 +482,10 @@ int mgp_logprob_tcz_launch(const float* xhat, const void* bh, const void* bl, co
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (D == 128) {
+    if (D == 256) {
+        MGP_CUDA(cudaFuncSetAttribute(logprob_z_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MGP_CUDA(cudaLaunchKernelEx(&cfg, logprob_z_kernel<256>, mx, mph, mpl, mout, prm));
+    } else if (D == 128) {
         MGP_CUDA(cudaFuncSetAttribute(logprob_z_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MGP_CUDA(cudaLaunchKernelEx(&cfg, logprob_z_kernel<128>, mx, mph, mpl, mout, prm));
     } else {

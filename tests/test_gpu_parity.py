@@ -339,10 +339,12 @@ def test_logprob_tc_vs_fp32(shape, sigma_mode):
         torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 if layout != 2 else 1e-12)
 
 
-@pytest.mark.parametrize("shape", [(3, 49, 130, 64), (5, 196, 2000, 128), (2, 200, 257, 128), (1, 7, 5, 128), (9, 196, 1000, 64)])
+@pytest.mark.parametrize("shape", [(3, 49, 130, 64), (5, 196, 2000, 128), (2, 200, 257, 128), (1, 7, 5, 128), (9, 196, 1000, 64),
+                                   (2, 196, 300, 256), (7, 49, 2000, 256), (1, 7, 5, 256)])
 def test_logprob_tmem_resident_kernel_vs_fp64(shape):
     """compute_log_prob's [N,P] kernel with the patch tile resident in tensor memory and the fp16 hi/lo split fused
-    (csrc/logprob_tcz.cu; taken by math='auto' when sigma is isotropic, D <= 128): ragged tiles on both sides, against
+    (csrc/logprob_tcz.cu; taken by math='auto' when sigma is isotropic, D <= 256 -- D = 256 keeps ONE operand buffer in
+    tensor memory and lands / converts the patch tile in two halves): ragged tiles on both sides, against
     float64 and against the kernel that splits x in a pre-pass (csrc/logprob_tc.cu)."""
     from mgproto_b200 import ops, _lib
     lib = _lib.load()

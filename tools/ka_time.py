@@ -14,7 +14,7 @@ from mgproto_b200 import _lib, ops                 # noqa: E402
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
 lib = _lib.load()
-B, HW, P, D = 256, 196, 2000, 128
+B, HW, P, D = 256, 196, 2000, int(os.environ.get("KA_D", "128"))
 N = B * HW
 g = torch.Generator().manual_seed(0)
 xs = [F.normalize(torch.randn(N, D, generator=g), dim=1).to(dev) for _ in range(6)]

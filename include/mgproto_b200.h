@@ -45,6 +45,12 @@ extern "C" {
                                Extends the tensor-core path to D = 256; the kernel traps if the
                                assertion is false                                               */
 #define MGP_MATH_TC_ISO_REUSE 5 /* TC_ISO with the prototype-side operands already in ws (as TC_REUSE) */
+/* OR-ed onto MGP_MATH_TC / _AUTO / _TC_ISO: the patch-side operands of `ws` (fp16 hi / lo split, |xhat|^2) were
+ * written by mgp_normalize_fwd_stage for exactly this xhat_nd -- the tensor-core kernels that read staged patches skip
+ * their own pre-pass (the TMEM-resident kernel reads fp32 xhat_nd and ignores the flag).  _ISO: staged with
+ * stage_aniso = 0, i.e. without the x^2 half an anisotropic sigma needs: the kernel faults if sigma turns out to be. */
+#define MGP_MATH_X_STAGED 0x100
+#define MGP_MATH_X_STAGED_ISO 0x200
 
 /* output layouts of mgp_logprob_fwd */
 #define MGP_OUT_LOGP_NP 0      /* out[n*P + p]           = log p      (ref: compute_log_prob)   */
@@ -80,6 +86,13 @@ int mgp_debug_set_ptr(const char* key, void* p, int arg);
  * first return value). */
 int mgp_normalize_fwd(const float* x_nchw, float* xhat_nd, float* inv_norm, float* xhat_nchw,
                       int B, int D, int HW, void* stream);
+/* The same pass, also writing the patch-side operands of the tensor-core log-likelihood kernels into `ws` (a workspace
+ * of mgp_logprob_ws_bytes(B, HW, P, D, MGP_MATH_TC) bytes that the following mgp_logprob_fwd call receives with
+ * MGP_MATH_X_STAGED[_ISO] OR-ed onto its math mode): one read of the features instead of two, one launch less.
+ * stage_aniso = 0 skips the x^2 half (only needed when some sigma varies over d). */
+int mgp_normalize_fwd_stage(const float* x_nchw, float* xhat_nd, float* inv_norm, float* xhat_nchw,
+                            void* ws, size_t ws_bytes, int B, int D, int HW, int P, int stage_aniso,
+                            void* stream);
 
 /* Backward of the above: g_xhat_nd [N,D] -> g_x_nchw [B,D,HW]
  *   g_x = (g - xhat * <xhat, g>) * inv_norm. */
@@ -294,6 +307,11 @@ int mgp_mine_ce(const float* out, const int64_t* gt, float* loss_b, float* grad,
  * logp_bphw [B,P,HW] -> arg [B,K] int32, val [B,K]. */
 int mgp_push_argmin(const float* logp_bphw, const int64_t* labels, int32_t* arg, float* val,
                     int B, int HW, int C, int K, void* stream);
+/* The same result from best_bp [B,P], the packed per-(image, prototype) max / arg-max of log p that
+ * mgp_logprob_fwd(..., MGP_OUT_TOP1_BP) computes in the tensor-core epilogue: the [B,P,HW] map (401 MB per batch of
+ * 256 at cfg2; the reference copies it to the host, push.py:109-118) is never formed. */
+int mgp_push_argmin_top1(const unsigned long long* best_bp, const int64_t* labels, int32_t* arg,
+                         float* val, int B, int C, int K, void* stream);
 
 #ifdef __cplusplus
 }

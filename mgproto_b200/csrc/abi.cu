@@ -10,7 +10,7 @@ bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D, int assum
 size_t mgp_logprob_tc_ws_bytes(long long N, int P, int D);
 int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log,
                           float* out, int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes,
-                          int reuse_operands, int assume_iso, cudaStream_t st);
+                          int reuse_operands, int assume_iso, int x_staged, cudaStream_t st);
 
 extern "C" int mgp_abi_version(void) { return MGP_ABI_VERSION; }
 
@@ -113,6 +113,9 @@ extern "C" int mgp_logprob_ws_is_prototype_only(int out_layout, int P, int D, in
 extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const float* sigma, float eps, float eps_log,
                                float* out, int out_layout, int B, int HW, int P, int D, int math, void* ws,
                                size_t ws_bytes, void* stream) {
+    // MGP_MATH_X_STAGED / MGP_MATH_X_STAGED_ISO: the patch-side operands of `ws` were written by mgp_normalize_fwd_stage
+    const int x_staged = (math & MGP_MATH_X_STAGED_ISO) ? 1 : ((math & MGP_MATH_X_STAGED) ? 2 : 0);
+    math &= 0xff;
     if (!xhat_nd || !mu || !sigma || !out || !ws) return MGP_ERR_INVALID;
     if (B <= 0 || HW <= 0 || P <= 0 || D <= 0 || (D & 3)) return MGP_ERR_INVALID;
     if (out_layout < MGP_OUT_LOGP_NP || out_layout > MGP_OUT_TOP1_BP) return MGP_ERR_INVALID;
@@ -127,7 +130,7 @@ extern "C" int mgp_logprob_fwd(const float* xhat_nd, const float* mu, const floa
     if (math == MGP_MATH_TC || math == MGP_MATH_AUTO || math == MGP_MATH_TC_REUSE || iso_mode) {
         if (mgp_logprob_tc_supported(out_layout, B, HW, P, D, iso_mode))
             return mgp_logprob_tc_launch(xhat_nd, mu, sigma, eps, eps_log, out, out_layout, B, HW, P, D, ws, ws_bytes,
-                                         math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO_REUSE, iso_mode, st);
+                                         math == MGP_MATH_TC_REUSE || math == MGP_MATH_TC_ISO_REUSE, iso_mode, x_staged, st);
         if (math != MGP_MATH_AUTO) return MGP_ERR_UNSUPPORTED;
     }
 #else

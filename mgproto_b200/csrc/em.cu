@@ -96,12 +96,13 @@ em_plan_kernel(uint8_t* __restrict__ updated, const int64_t* __restrict__ mem_le
         for (int i = threadIdx.x; i <= n; i += blockDim.x) {
             if (i < n) {
                 const double t = (double)(s0 + i + 1);
-                bias_corr[2 * i] = (float)(adam.lr / (1.0 - pow(adam.beta1, t)));
-                bias_corr[2 * i + 1] = (float)sqrt(1.0 - pow(adam.beta2, t));
+                bias_corr[2 * i] = (float)(adam.lr / (1.0 - exp(t * adam.ln_b1)));
+                bias_corr[2 * i + 1] = (float)sqrt(1.0 - exp(t * adam.ln_b2));
             }
-            t_b1[i] = (float)pow(adam.beta1, (double)i);
-            t_b2h[i] = (float)pow(adam.beta2, 0.5 * (double)i);
-            t_b2[i] = (float)pow(adam.beta2, (double)i);
+            const double b2h = exp(0.5 * (double)i * adam.ln_b2);
+            t_b1[i] = (float)exp((double)i * adam.ln_b1);
+            t_b2h[i] = (float)b2h;
+            t_b2[i] = (float)(b2h * b2h);
         }
     }
 }

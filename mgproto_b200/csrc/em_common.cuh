@@ -1,5 +1,6 @@
 // Shared by em.cu and em_tc.cu: Adam configuration, the closed-form zero-gradient replay, one Adam step.
 #pragma once
+#include <math.h>
 #include "mgp_common.cuh"
 
 namespace mgp_em {
@@ -12,11 +13,13 @@ constexpr float EM_EPS = 1e-10f;
 // would be off by 1.3e-5 relative.  The C ABI therefore carries them as doubles and the fp32 factors are derived here.
 struct AdamCfg {
     double lr, beta1, beta2, eps;
+    double ln_b1, ln_b2;            // log(beta) evaluated on the host: the planner's tables are exp(t ln b), not pow(b, t)
     float b2f, omb1, omb2, epsf;
 };
 static inline AdamCfg make_adam(double lr, double beta1, double beta2, double eps) {
     AdamCfg a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    a.ln_b1 = (beta1 > 0.0) ? log(beta1) : -1e300; a.ln_b2 = (beta2 > 0.0) ? log(beta2) : -1e300;
     a.b2f = (float)beta2; a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2); a.epsf = (float)eps;
     return a;
 }

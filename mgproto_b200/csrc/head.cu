@@ -849,6 +849,20 @@ __global__ void push_argmin_kernel(const float* __restrict__ logp, const int64_t
     }
 }
 
+// f1 without the log p matrix: the same (arg, val) from the packed per-(image, prototype) max / arg-max that the
+// tensor-core epilogue leaves in `best` (MGP_OUT_TOP1_BP; ties already resolved towards the first patch).
+__global__ void push_from_top1_kernel(const unsigned long long* __restrict__ best, const int64_t* __restrict__ labels,
+                                      int32_t* __restrict__ arg, float* __restrict__ val, int B, int C, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * K) return;
+    const int b = i / K, k = i - b * K;
+    const long long c = labels[b];
+    if (c < 0 || c >= C) { arg[i] = -1; val[i] = 0.f; return; }
+    const unsigned long long pk = best[(size_t)b * C * K + (size_t)c * K + k];
+    arg[i] = (int)(0xffffffffu - (unsigned)(pk & 0xffffffffull));
+    val[i] = -expf(key2f((unsigned)(pk >> 32)));
+}
+
 }  // namespace
 
 static int head_select_launch(const float* logp, int from_np, const float* weight_cp, const int64_t* gt, float* logits,
@@ -1053,6 +1067,14 @@ extern "C" int mgp_push_argmin(const float* logp_bphw, const int64_t* labels, in
     if (!logp_bphw || !labels || !arg || !val || B <= 0 || HW <= 0 || C <= 0 || K <= 0) return MGP_ERR_INVALID;
     const int warps = B * K;
     push_argmin_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logp_bphw, labels, arg, val, HW, C, K, B);
+    MGP_CHECK_LAUNCH();
+    return MGP_OK;
+}
+
+extern "C" int mgp_push_argmin_top1(const unsigned long long* best_bp, const int64_t* labels, int32_t* arg, float* val, int B,
+                                    int C, int K, void* stream) {
+    if (!best_bp || !labels || !arg || !val || B <= 0 || C <= 0 || K <= 0) return MGP_ERR_INVALID;
+    push_from_top1_kernel<<<(B * K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(best_bp, labels, arg, val, B, C, K);
     MGP_CHECK_LAUNCH();
     return MGP_OK;
 }

@@ -151,6 +151,7 @@ struct TcParams {
     int team;              // CTAs per team: the CTAs of a team work on the SAME x tile at the same time, on
                            // adjacent prototype tiles, so each output row receives team*512 contiguous bytes at once
     uint32_t smem_bytes;   // dynamic shared memory of the launch
+    int x_no_sq;           // the staged patch operands lack the x^2 half (isotropic sigma asserted by the producer)
     int debug;   // ablation switches for profiling (MGP_TC_DEBUG): 1 no global stores, 2 no TMEM loads, 4 no MMAs,
                  // 8 no epilogue work, 16 no prototype TMA loads
 };
@@ -307,7 +308,7 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     uint8_t* base_ptr = smem_raw + (base - raw);
 
     const bool gen = (*prm.noniso != 0);
-    if (gen && prm.D > 128) __trap();                             // MGP_MATH_TC_ISO promised isotropic sigma: fail loudly
+    if (gen && (prm.D > 128 || prm.x_no_sq)) __trap();            // isotropic sigma was promised (MGP_MATH_TC_ISO / staging): fail loudly
     const int nkb = (gen ? 2 * prm.D : prm.D) / KB;               // K blocks per tile
     const int kcol0 = gen ? 0 : prm.D;                            // isotropic: only the [x] / [-2 w mu] half
     // [B,P,HW] through TMA: one x tile = one image (nti = round_up(HW,32) columns, UMMA N = nti) so that no
@@ -316,7 +317,9 @@ logprob_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     const bool img = (BPHW_TMA || (LAYOUT == LAYOUT_TOP1 && prm.xbox == 32)) && !gen;
     const int NT = img ? prm.nti : 128;                           // patches per tile = UMMA N
     const int row_step = img ? prm.HW : 128;                      // first patch row of x tile nt = nt * row_step
-    const uint32_t idesc = make_idesc(NT);
+    // image tiles: the x tile holds nti = round_up(HW, 32) rows (whole 32-row TMA boxes), the MMA only spans
+    // round_up(HW, 16) of them (HW = 196: N = 208 instead of 224); the columns beyond are never read (masked / clipped)
+    const uint32_t idesc = make_idesc(img ? ((prm.HW + 15) & ~15) : NT);
     const int n_ptiles = prm.n_ptiles, n_ntiles = img ? prm.B : prm.n_ntiles;
     const uint32_t xsub = (uint32_t)NT * KB * 2;                  // one [NT x 64] fp16 block of the x tile
 
@@ -603,9 +606,20 @@ bool mgp_logprob_tc_supported(int layout, int B, int HW, int P, int D, int assum
 
 size_t mgp_logprob_tc_ws_bytes(long long N, int P, int D) { return ws_layout(N, P, D).total; }
 
+// the patch-side operand slots of the workspace, for a producer that writes them itself (mgp_normalize_fwd_stage)
+bool mgp_logprob_tc_stage_ptrs(void* ws, size_t ws_bytes, long long N, int P, int D, __half** ah, __half** al, float** sn) {
+    const WsLayout w = ws_layout(N, P, D);
+    if (!ws || ws_bytes < w.total) return false;
+    uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+    *ah = reinterpret_cast<__half*>(wsb + w.ah);
+    *al = reinterpret_cast<__half*>(wsb + w.al);
+    *sn = reinterpret_cast<float*>(wsb + w.sn);
+    return true;
+}
+
 int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma, float eps, float eps_log, float* out,
                           int layout, int B, int HW, int P, int D, void* ws, size_t ws_bytes, int reuse_operands,
-                          int assume_iso, cudaStream_t st) {
+                          int assume_iso, int x_staged, cudaStream_t st) {
     const long long N = (long long)B * HW;
     const WsLayout w = ws_layout(N, P, D);
     if (ws_bytes < w.total) return MGP_ERR_WORKSPACE;
@@ -626,7 +640,7 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
         MGP_CUDA(cudaMemsetAsync(flag, 0, 4, st));
         tc_proto_prep_kernel<<<(P + 7) / 8, 256, 0, st>>>(mu, sigma, eps, eps_log, bh, bl, e0, e1, e2, flag, P, D);
         MGP_CHECK_LAUNCH();
-        if (!use_z) {
+        if (!use_z && !(x_staged & 1)) {
             tc_x_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(xhat, ah, al, sn, flag, (int)N, D);
             MGP_CHECK_LAUNCH();
         }
@@ -658,6 +672,7 @@ int mgp_logprob_tc_launch(const float* xhat, const float* mu, const float* sigma
     TcParams prm;
     prm.e0 = e0; prm.e1 = e1; prm.e2 = e2; prm.sn = sn; prm.noniso = flag; prm.out = out;
     prm.N = (int)N; prm.HW = HW; prm.P = P; prm.D = D;
+    prm.x_no_sq = (x_staged == 1) ? 1 : 0;          // staged without the x^2 half: an anisotropic sigma must fault, not read stale data
     {
         const char* dbg = getenv("MGP_TC_DEBUG");
         prm.debug = dbg ? atoi(dbg) : 0;

@@ -228,10 +228,20 @@ class MGProto(nn.Module):
         -> (arg [B,K] int32, val [B,K], xhat [N,D])."""
         C, K, D = self.prototype_means.shape
         B, _, H, W = x_add.shape
-        xhat, _, _ = ops.normalize_fwd(x_add.contiguous())
-        lp = ops.logprob(xhat, self.prototype_means.detach().reshape(C * K, D),
-                         self.prototype_covs.detach().reshape(C * K, D), MGP_OUT_LOGP_BPHW, B=B, HW=H * W,
-                         math=self.math_mode)
+        mu = self.prototype_means.detach().reshape(C * K, D)
+        sg = self.prototype_covs.detach().reshape(C * K, D)
+        # the max / arg-max epilogue of the tensor-core kernel already is the per-prototype search: no [B,P,HW] map at all
+        stage = ops._stage_for_top1(B, H * W, C * K, D, sg, self.math_mode)
+        if stage is not None:
+            xhat, _, _, ws = ops.normalize_fwd(x_add.contiguous(), stage=stage)
+            best = ops.logprob_top1(xhat, mu, sg, B, H * W, self.math_mode, ws=ws, staged=stage)
+        else:
+            xhat, _, _ = ops.normalize_fwd(x_add.contiguous())
+            best = ops.logprob_top1(xhat, mu, sg, B, H * W, self.math_mode)
+        if best is not None:
+            arg, val = ops.push_argmin_top1(best, labels.contiguous(), C, K)
+            return arg, val, xhat
+        lp = ops.logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=H * W, math=self.math_mode)
         arg, val = ops.push_argmin(lp, labels.contiguous(), C, K)
         return arg, val, xhat
 

@@ -13,11 +13,12 @@ import torch
 
 from . import _lib
 from ._lib import (MGP_MATH_AUTO, MGP_MATH_FP32, MGP_MATH_TC, MGP_MATH_TC_ISO, MGP_MATH_TC_ISO_REUSE, MGP_MATH_TC_REUSE,
+                   MGP_MATH_X_STAGED, MGP_MATH_X_STAGED_ISO,
                    MGP_OUT_LOGP_BPHW,
                    MGP_OUT_LOGP_NP, MGP_OUT_NEGP_BPHW, MGP_OUT_TOP1_BP, check)
 
 __all__ = ["normalize_fwd", "logprob", "logprob_top1", "head_select", "head_select_top1", "head_level0", "head_forward", "HeadFunction", "mined_gather", "bank_enqueue",
-           "bank_linearize", "bank_shadow_sync", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "em_mstep_div", "topt_pool", "ood_score", "push_argmin", "mine_cross_entropy",
+           "bank_linearize", "bank_shadow_sync", "em_plan", "em_stats", "em_update", "update_gmm", "em_estep", "em_mstep_closed", "em_mstep_div", "topt_pool", "ood_score", "push_argmin", "push_argmin_top1", "mine_cross_entropy",
            "MATH_MODES"]
 
 MATH_MODES = {"fp32": MGP_MATH_FP32, "tc": MGP_MATH_TC, "auto": MGP_MATH_AUTO, "tc_reuse": MGP_MATH_TC_REUSE,
@@ -32,11 +33,13 @@ _PROTO_OPERANDS = collections.OrderedDict()   # (mu, sigma identity + version, s
 def sigma_is_isotropic(sigma: torch.Tensor) -> bool:
     """True if sigma is constant over the feature dim inside every prototype.  One tiny device reduction + host
     read, cached per (storage, version): sigma never changes in the reference's training loop."""
-    key = (sigma.data_ptr(), sigma._version, tuple(sigma.shape))
+    # ([C,K,D] and its [P,D] view are the same question: the key leaves the leading shape out)
+    key = (sigma.data_ptr(), sigma._version, sigma.numel(), sigma.shape[-1], str(sigma.device))
     hit = _iso_cache.get(key)
     if hit is None:
         hit = bool((sigma == sigma[..., :1]).all().item())
-        _iso_cache.clear()
+        if len(_iso_cache) >= 8:
+            _iso_cache.clear()
         _iso_cache[key] = hit
     return hit
 
@@ -130,8 +133,10 @@ def _math(math) -> int:
 
 # ----------------------------------------------------------------------------------- a1
 @_on_device
-def normalize_fwd(x_bdhw: torch.Tensor, want_nchw: bool = False):
-    """ref model.py:210-211.  -> (xhat [N,D], inv_norm [N], xhat_nchw [B,D,H,W] | None)."""
+def normalize_fwd(x_bdhw: torch.Tensor, want_nchw: bool = False, stage=None):
+    """ref model.py:210-211.  -> (xhat [N,D], inv_norm [N], xhat_nchw [B,D,H,W] | None).
+    stage = (P, aniso): also write the patch-side operands of the tensor-core log-likelihood kernels in the same pass
+    (mgp_normalize_fwd_stage) -> a 4th return value: the workspace to hand to logprob_top1(..., staged=...)."""
     x = _req(x_bdhw, torch.float32, "x")
     B, D, H, W = x.shape
     HW = H * W
@@ -139,10 +144,29 @@ def normalize_fwd(x_bdhw: torch.Tensor, want_nchw: bool = False):
     inv = torch.empty((B * HW,), device=x.device, dtype=torch.float32)
     nchw = torch.empty_like(x) if want_nchw else None
     lib = _lib.load()
+    if stage is not None:
+        P, aniso = stage
+        nbytes = lib.mgp_logprob_ws_bytes(B, HW, int(P), D, MGP_MATH_TC)
+        ws = torch.empty((max(16, nbytes),), device=x.device, dtype=torch.uint8)
+        check(lib.mgp_normalize_fwd_stage(x.data_ptr(), xhat.data_ptr(), inv.data_ptr(), _p(nchw), ws.data_ptr(), nbytes,
+                                          B, D, HW, int(P), 1 if aniso else 0, _stream()), "mgp_normalize_fwd_stage")
+        _count(1)
+        return xhat, inv, nchw, ws
     check(lib.mgp_normalize_fwd(x.data_ptr(), xhat.data_ptr(), inv.data_ptr(), _p(nchw), B, D, HW, _stream()),
           "mgp_normalize_fwd")
     _count(1)
     return xhat, inv, nchw
+
+
+def _stage_for_top1(B, HW, P, D, sg, math):
+    """(P, aniso) if the labelled head's max / arg-max kernel will read staged patch operands for this shape and math
+    mode (tensor-core path, D <= 128: csrc/logprob_tc.cu), else None."""
+    m = _math(math)
+    if m not in (MGP_MATH_AUTO, MGP_MATH_TC, MGP_MATH_TC_ISO) or D not in (64, 128) or HW < 32 or HW > 256:
+        return None
+    if not _lib.load().mgp_has_tensor_core_path():
+        return None
+    return (P, not sigma_is_isotropic(sg))
 
 
 # ----------------------------------------------------------------------------------- a2/a3/a16
@@ -207,10 +231,11 @@ def logprob(xhat_nd, mu_pd, sigma_pd, layout=MGP_OUT_LOGP_NP, B=None, HW=None, e
 
 
 @_on_device
-def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto", ws=None, return_ws=False):
+def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto", ws=None, return_ws=False, staged=None):
     """Per (image, prototype) max / arg-max of log p over the patches, computed in the tensor-core kernel's
     epilogue without writing log p (MGP_OUT_TOP1_BP).  -> packed int64 [B,P] (see include/mgproto_b200.h), or None
-    when the tensor-core path does not cover the shape / math mode (the caller then materialises log p)."""
+    when the tensor-core path does not cover the shape / math mode (the caller then materialises log p).
+    staged = (P, aniso) as given to normalize_fwd(stage=...), with its workspace in `ws`: the patch pre-pass is skipped."""
     x = _req(xhat_nd, torch.float32, "xhat")
     mu = _req(mu_pd, torch.float32, "mu")
     sg = _req(sigma_pd, torch.float32, "sigma")
@@ -230,12 +255,15 @@ def logprob_top1(xhat_nd, mu_pd, sigma_pd, B, HW, math="auto", ws=None, return_w
     elif ws.numel() < nbytes:
         raise RuntimeError("mgproto_b200: workspace too small")
     best = torch.empty((B, P), device=x.device, dtype=torch.int64)
+    flag = 0
+    if staged is not None and ws is not None:
+        flag = MGP_MATH_X_STAGED if staged[1] else MGP_MATH_X_STAGED_ISO
     rc = lib.mgp_logprob_fwd(x.data_ptr(), mu.data_ptr(), sg.data_ptr(), 0.0, 0.0, best.data_ptr(), MGP_OUT_TOP1_BP,
-                             B, HW, P, D, m, ws.data_ptr(), nbytes, _stream())
+                             B, HW, P, D, m | flag, ws.data_ptr(), nbytes, _stream())
     if rc == -2:                                      # MGP_ERR_UNSUPPORTED: no tensor-core path for this shape
         return None
     check(rc, "mgp_logprob_fwd(top1)")
-    _count(1 if m == MGP_MATH_TC_REUSE else 3)
+    _count(1 if m == MGP_MATH_TC_REUSE else (2 if flag else 3))
     return (best, ws) if return_ws else best
 
 
@@ -307,11 +335,16 @@ class HeadFunction(torch.autograd.Function):
         mu = mu_ckd.detach().reshape(C * K, D).contiguous()
         sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
         wt = weight_cp.detach().contiguous()
-        xhat, inv, _ = normalize_fwd(x_add)
         # the labelled fast path needs the tensor-core kernel and head_top1_kernel's shared-memory layout to fit
         top1_smem = (2 * C * K + K * T + K * (HW + 1) + 2 * K * D + 2 * K + 4) * 4
         use_top1 = gt is not None and T <= min(32, HW) and HW <= 1024 and top1_smem <= 200 * 1024
-        best = logprob_top1(xhat, mu, sg, B, HW, math) if use_top1 else None
+        stage = _stage_for_top1(B, HW, C * K, D, sg, math) if use_top1 else None
+        if stage is not None:       # one pass: normalise + the fp16 hi/lo operands the max / arg-max kernel reads
+            xhat, inv, _, ws1 = normalize_fwd(x_add, stage=stage)
+            best = logprob_top1(xhat, mu, sg, B, HW, math, ws=ws1, staged=stage)
+        else:
+            xhat, inv, _ = normalize_fwd(x_add)
+            best = logprob_top1(xhat, mu, sg, B, HW, math) if use_top1 else None
         if best is not None:
             # labelled step: log p never reaches HBM (wrong-class prototypes only need their max, ref model.py:218-221)
             logits, vals, idx = head_select_top1(best, xhat, mu, sg, wt, _req(gt, torch.int64, "gt"), T, C, K, HW)
@@ -362,9 +395,14 @@ def head_level0(x_add, mu_ckd, sigma_ckd, weight_cp, math="auto"):
         mu = mu_ckd.detach().reshape(C * K, D).contiguous()
         sg = sigma_ckd.detach().reshape(C * K, D).contiguous()
         wt = weight_cp.detach().contiguous()
-        xhat, _, _ = normalize_fwd(x_add.detach().contiguous())
         fits = HW <= 1024 and (2 * C * K + 2 * K + K * (HW + 1) + 2 * K * D + 2 * K + 4) * 4 <= 200 * 1024
-        best = logprob_top1(xhat, mu, sg, B, HW, math) if fits else None
+        stage = _stage_for_top1(B, HW, C * K, D, sg, math) if fits else None
+        if stage is not None:
+            xhat, _, _, ws1 = normalize_fwd(x_add.detach().contiguous(), stage=stage)
+            best = logprob_top1(xhat, mu, sg, B, HW, math, ws=ws1, staged=stage)
+        else:
+            xhat, _, _ = normalize_fwd(x_add.detach().contiguous())
+            best = logprob_top1(xhat, mu, sg, B, HW, math) if fits else None
         if best is None:
             lp = logprob(xhat, mu, sg, MGP_OUT_LOGP_BPHW, B=B, HW=HW, math=math)
             return head_select(lp, wt, None, 1, C, K)[0][:, :, 0]
@@ -660,6 +698,20 @@ def mine_cross_entropy(out, gt, mine_coef=0.2):
 
 
 # ----------------------------------------------------------------------------------- f1
+@_on_device
+def push_argmin_top1(best_bp, labels, C, K):
+    """ref push.py:125-158 from the packed top-1 results of logprob_top1 -> (arg [B,K] int32, val [B,K] = -p there)."""
+    best = _req(best_bp, torch.int64, "best")
+    lab = _req(labels, torch.int64, "labels")
+    B = best.shape[0]
+    arg = torch.empty((B, K), device=best.device, dtype=torch.int32)
+    val = torch.empty((B, K), device=best.device, dtype=torch.float32)
+    check(_lib.load().mgp_push_argmin_top1(best.data_ptr(), lab.data_ptr(), arg.data_ptr(), val.data_ptr(), B, C, K,
+                                           _stream()), "mgp_push_argmin_top1")
+    _count(1)
+    return arg, val
+
+
 @_on_device
 def push_argmin(logp_bphw, labels, C, K):
     """ref push.py:125-158 -> (arg [B,K] int32 flat HW index, val [B,K] = -p at the argmin)."""

@@ -512,6 +512,39 @@ def test_logprob_tc_bphw_tma_path():
         torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 if layout == 1 else 1e-12)
 
 
+def test_push_search_from_the_top1_epilogue_vs_materialised_map():
+    """f1 without the [B,P,HW] map: push_search through mgp_push_argmin_top1 (packed max / arg-max of the tensor-core
+    epilogue) against mgp_push_argmin on the materialised fp32 map and against float64."""
+    import mgproto_b200 as M
+    from mgproto_b200 import ops, _lib
+    if not _lib.load().mgp_has_tensor_core_path():
+        pytest.skip("library built without the tcgen05 path")
+    C, K, D, H, W, B = 12, 10, 128, 14, 14, 6
+    torch.manual_seed(9)
+    net = M.MGProto(features=nn.Sequential(nn.Conv2d(3, 16, 1)), img_size=H, prototype_shape=(C * K, D, 1, 1),
+                    proto_layer_rf_info=None, num_classes=C, add_on_layers_type="regular", sz_embedding=8,
+                    mem_capacity=8, mine_K=4).to(_dev())
+    g = torch.Generator().manual_seed(10)
+    x_add = torch.randn(B, D, H, W, generator=g).to(_dev())
+    labs = torch.randint(0, C, (B,), generator=g).to(_dev())
+    labs[0] = -1                                                   # no valid class: arg -1, val 0 (as mgp_push_argmin)
+    n0 = ops.launch_count()
+    arg, val, xhat = net.push_search(x_add, labs)
+    assert ops.launch_count() - n0 <= 4                            # normalise+stage, prototype pre-pass + GEMM, gather
+    lp = ops.logprob(xhat, net.prototype_means.detach().reshape(C * K, D), net.prototype_covs.detach().reshape(C * K, D),
+                     1, B=B, HW=H * W, math="fp32")
+    arg0, val0 = ops.push_argmin(lp, labs, C, K)
+    torch.testing.assert_close(val, val0, rtol=RTOL, atol=1e-30)
+    lp64 = lp.double().cpu().numpy()
+    a, a0 = arg.cpu().numpy(), arg0.cpu().numpy()
+    assert (a[0] == -1).all() and float(val[0].abs().max()) == 0.0
+    for b in range(1, B):
+        c = int(labs[b])
+        for k in range(K):
+            row = lp64[b, c * K + k]
+            assert a[b, k] == a0[b, k] or row[a[b, k]] >= row.max() - 1e-4 * abs(row.max())
+
+
 def test_push_prototypes_matches_oracle():
     """Prototype projection (push.py:82-200, numeric half) on a synthetic push set: chosen (image, patch) per
     prototype and the copied feature vectors against the oracle run on the distance maps of push_forward."""
@@ -588,6 +621,19 @@ def test_fused_top1_path_vs_materialised(B, H, W, C, K, D, T, aniso):
     srt = torch.sort(lp64, dim=2, descending=True).values
     sep = ((srt[:, :, 0] - srt[:, :, 1]) > 1e-3).cpu().numpy()
     assert (arg[sep] == a64.cpu().numpy()[sep]).all()
+    # the same through the fused normalise + operand staging pass (what HeadFunction runs when 32 <= HW <= 256)
+    stage = ops._stage_for_top1(B, HW, P, D, sg2, "tc")
+    if stage is not None:
+        assert stage[1] == aniso
+        xh2, inv2, _, ws = ops.normalize_fwd(x, stage=stage)
+        assert torch.equal(xh2, xhat)
+        best2 = ops.logprob_top1(xh2, mu2, sg2, B, HW, "tc", ws=ws, staged=stage)
+        b2 = best2.cpu().numpy().astype(np.uint64)
+        k2 = (b2 >> np.uint64(32)).astype(np.uint32)
+        u2 = np.where(k2 & np.uint32(0x80000000), k2 & np.uint32(0x7fffffff), ~k2).astype(np.uint32)
+        np.testing.assert_allclose(u2.view(np.float32), val, rtol=1e-6, atol=1e-6)    # (|xhat|^2 is summed in another order)
+        arg2 = (np.uint32(0xffffffff) - (b2 & np.uint64(0xffffffff)).astype(np.uint32)).astype(np.int64)
+        assert (arg2[sep] == a64.cpu().numpy()[sep]).all()
     # whole head, both routes
     lg1, v1, i1 = ops.head_select_top1(best, xhat, mu2, sg2, wt, gt, T, C, K, HW)
     lp = ops.logprob(xhat, mu2, sg2, 1, B=B, HW=HW, math="tc")

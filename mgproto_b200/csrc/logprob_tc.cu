@@ -170,10 +170,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         const float4 s = s4[j4];
-        v[4 * j4 + 0] = fmaf(c1, __uint_as_float(r[4 * j4 + 0]), fmaf(c2, s.x, c0));
-        v[4 * j4 + 1] = fmaf(c1, __uint_as_float(r[4 * j4 + 1]), fmaf(c2, s.y, c0));
-        v[4 * j4 + 2] = fmaf(c1, __uint_as_float(r[4 * j4 + 2]), fmaf(c2, s.z, c0));
-        v[4 * j4 + 3] = fmaf(c1, __uint_as_float(r[4 * j4 + 3]), fmaf(c2, s.w, c0));
+        // two columns per FFMA2 (same rounding as two scalar fmaf: each half is an IEEE fused multiply-add)
+        const float2 c00 = make_float2(c0, c0), c11 = make_float2(c1, c1), c22 = make_float2(c2, c2);
+        const float2 v01 = ffma2(c11, make_float2(__uint_as_float(r[4 * j4 + 0]), __uint_as_float(r[4 * j4 + 1])),
+                                 ffma2(c22, make_float2(s.x, s.y), c00));
+        const float2 v23 = ffma2(c11, make_float2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])),
+                                 ffma2(c22, make_float2(s.z, s.w), c00));
+        v[4 * j4 + 0] = v01.x; v[4 * j4 + 1] = v01.y; v[4 * j4 + 2] = v23.x; v[4 * j4 + 3] = v23.y;
     }
     if (LAYOUT == LAYOUT_TOP1) {
         // only max_n log p[n, p] and its patch per image are wanted (labelled training step: the reference aliases
@@ -181,16 +184,28 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const fl
         // never reaches HBM.  Image tiles keep a running (max, patch) across the warp's chunks (the caller issues
         // one 64-bit RED.MAX per tile); 128-patch tiles may cross image ends and reduce per image segment.
         if (img) {
-            float mv = *run_v;
-            int mi = *run_i;
+            // chunk maximum by a tree of FMNMX (one instruction per column); the position is only looked up when the
+            // chunk beats the running maximum (a few times per image): same result as the strict left-to-right scan
+            // (first patch wins ties) at ~2 instead of ~5 instructions per column
+            if (img_hw0 + 32 > HW) {                              // the image's last chunk: columns beyond HW do not exist
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const bool better = (img_hw0 + j < HW) && (v[j] > mv);
-                mv = better ? v[j] : mv;
-                mi = better ? img_hw0 + j : mi;
+                for (int j = 0; j < 32; ++j)
+                    if (img_hw0 + j >= HW) v[j] = -INFINITY;
             }
-            *run_v = mv;
-            *run_i = mi;
+            float m[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
+            if (m[0] > *run_v) {
+                int idx = 31;
+#pragma unroll
+                for (int j = 30; j >= 0; --j) idx = (v[j] == m[0]) ? j : idx;
+                *run_v = m[0];
+                *run_i = img_hw0 + idx;
+            }
             return;
         }
         if (!pok) return;

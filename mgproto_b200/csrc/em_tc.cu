@@ -36,7 +36,6 @@ constexpr float SX = 256.0f;      // shadow rows hold 256 x (fp16 hi + lo)
 constexpr float SR = 1024.0f;     // responsibilities are stored as 1024 r
 constexpr int TR = 128;           // bank rows per tile (UMMA M of the E-step, K extent of the statistics GEMM)
 constexpr int NK = 16;            // UMMA N: components padded to 16
-constexpr int TAB = 256;
 
 struct EmTcParams {
     const float* xx;              // [C*cap] |x|^2 of the bank rows (shadow)
@@ -107,9 +106,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(bp + o_misc);            // !PIPE: tma, estep, stats | PIPE: xfull[3] xfree[3] efull[2] rfull[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
     float* s_e = reinterpret_cast<float*>(bars + 12);                     // [KT][KT]
-    float* s_c = s_e + KT * KT;                                           // [TAB]
-    float* s_d = s_c + TAB;                                               // [TAB]
-    float* s_red = s_d + TAB;                                             // [8] + [8][16]
+    float* s_red = s_e + KT * KT;                                         // [8] + [8][16]
     float* s_w = s_red + 136;                                             // [16] w_k
     float* s_ls = s_w + 16;                                               // [16] sum_d (log(sigma+eps) + log(2pi)/2)
     float* s_pi = s_ls + 16;                                              // [16]
@@ -728,7 +725,7 @@ em_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ 
 template <int D>
 size_t em_tc_smem(int kt, bool pipe) {
     return 1024 + (pipe ? 3 : 1) * 2 * (size_t)(D / 64) * TR * 128 + (size_t)(D / 64) * 4096 + (pipe ? 2 : 1) * 8192 +
-           ((size_t)kt * kt + 2 * TAB + 136 + 6 * 16 + 8 + 8 * (size_t)(32 * ((kt * (kt - 1) / 2 + kt + 31) / 32))) * 4 + 128;
+           ((size_t)kt * kt + 136 + 6 * 16 + 8 + 8 * (size_t)(32 * ((kt * (kt - 1) / 2 + kt + 31) / 32))) * 4 + 128;
 }
 
 }  // namespace

@@ -699,6 +699,7 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                 };
                 auto walk = [&](auto aniso_tag) {
                     constexpr bool AN = decltype(aniso_tag)::value;
+                    constexpr int PF = (VEC == 4 && !AN) ? 16 : 8;    // prototype rows in flight per lane
                     for (int i0 = wb; i0 < we; i0 += 32) {
                         const int i = i0 + lane;
                         const bool ok = i < we;
@@ -706,17 +707,17 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                         const float av = ok ? sval[i] : 0.f;
                         const float v2 = (!AN && ok) ? av * __ldg(wsc + (kk >> 10)) : 0.f;
                         const int m = min(32, we - i0);
-                        for (int j0 = 0; j0 < m; j0 += 8) {
-                            LV fm[8], fw[8];
+                        for (int j0 = 0; j0 < m; j0 += PF) {
+                            LV fm[PF], fw[AN ? PF : 1];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
+                            for (int u = 0; u < PF; ++u) {
                                 const unsigned ku = __shfl_sync(0xffffffffu, kk, j0 + u);
                                 const unsigned po = (ku >> 10) * (unsigned)D;
                                 fm[u] = lv_ldg<VEC>(wmcol_l + po);
-                                if (AN) fw[u] = lv_ldg<VEC>(wcol_l + po);
+                                if constexpr (AN) fw[u] = lv_ldg<VEC>(wcol_l + po);
                             }
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
+                            for (int u = 0; u < PF; ++u) {
                                 const int n = (int)(__shfl_sync(0xffffffffu, kk, j0 + u) & 1023u);
                                 const float a = __shfl_sync(0xffffffffu, av, j0 + u);
                                 if (n != cur_n) {
@@ -733,7 +734,7 @@ head_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ logits, 
                                 }
 #pragma unroll
                                 for (int i = 0; i < VEC; ++i) s1.v[i] = fmaf(a, fm[u].v[i], s1.v[i]);
-                                if (AN) {
+                                if constexpr (AN) {
 #pragma unroll
                                     for (int i = 0; i < VEC; ++i) s2v.v[i] = fmaf(a, fw[u].v[i], s2v.v[i]);
                                 } else {

@@ -59,8 +59,13 @@ _op_device = None      # device of the op being issued: every tensor argument of
 _CHECK_ALL = os.environ.get("MGP_CHECK_DEVICES", "0") == "1"
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
     """Raw handle of the current stream OF THE OP'S DEVICE (not of whatever device happens to be current)."""
+    if _raw_stream is not None and _op_device is not None and _op_device.index is not None:
+        return _raw_stream(_op_device.index)                 # (no Stream object: ~10x cheaper, called once per launch)
     return torch.cuda.current_stream(_op_device).cuda_stream
 
 

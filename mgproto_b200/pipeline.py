@@ -78,3 +78,62 @@ class HostSink:
 
     def wait(self):
         self.stream.synchronize()
+
+
+class GraphedStep:
+    """The whole training step -- head forward, loss, backward, bank enqueue, update_GMM -- captured ONCE in a CUDA
+    graph and replayed per batch: the ~20 kernel launches of a step cost the host one ``cudaGraphLaunch`` instead of
+    ~400 us of Python / ctypes / dispatcher work, and the kernels run back to back.
+
+        step = GraphedStep(net, loss_fn, x0, gt0)     # runs `warmup` REAL steps on (x0, gt0), then captures one more
+        for x, gt in batches:
+            out, loss = step(x, gt)                   # x [B,D,H,W] features, gt [B] int64 (same shapes as x0, gt0)
+            # step.x_grad holds d loss / d x for the backbone (static buffer, overwritten by the next call)
+
+    Everything the step does on the host (version bumps, the optimiser-state bookkeeping of update_GMM) happens at
+    capture time only, so ``__call__`` re-announces the raw-pointer writes to torch after every replay.  The library's
+    kernels keep all step-dependent state (Adam step counter, bank cursors, update flags) on the device, which is what
+    makes the step replayable.  Shapes are fixed; with ``torch.distributed`` initialised the all-gather of the
+    multi-GPU exchange is captured with the rest (every rank must construct and call the step in lock-step).
+    """
+
+    def __init__(self, net, loss_fn, x_example: torch.Tensor, gt_example: torch.Tensor, warmup: int = 3):
+        self.net, self.loss_fn = net, loss_fn
+        dev = x_example.device
+        self.x = torch.empty_like(x_example).requires_grad_(True)
+        self.gt = torch.empty_like(gt_example)
+        with torch.no_grad():
+            self.x.copy_(x_example)
+            self.gt.copy_(gt_example)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # lazy initialisations (workspaces, shadows, device counters) happen here
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        from . import ops
+        n0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out, self.loss = self._body()
+        self.launches = ops.launch_count() - n0      # library kernels per replay (torch's own few are not counted)
+        self.x_grad = self.x.grad
+
+    def _body(self):
+        self.x.grad = None
+        out = self.net.head(self.x, self.gt)
+        loss = self.loss_fn(out, self.gt)
+        loss.backward()
+        self.net.update_GMM()
+        return out, loss
+
+    def __call__(self, x: torch.Tensor, gt: torch.Tensor):
+        with torch.no_grad():
+            self.x.copy_(x, non_blocking=True)
+            self.gt.copy_(gt, non_blocking=True)
+        self.graph.replay()
+        bump = getattr(self.net, "_bump_versions", None)
+        if bump is not None:
+            bump()
+        return self.out, self.loss

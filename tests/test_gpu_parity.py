@@ -840,3 +840,55 @@ def test_ood_scorer_device_side_vs_oracle_and_sklearn():
     y = np.r_[np.ones(n), np.zeros(n)]
     assert abs(res["AUROC"] - roc_auc_score(y, np.r_[ref_in.sum(1), ref_out.sum(1)])) < 1e-6
     assert abs(res["accuracy"] - float((ref_in.argmax(1) == lab.numpy()).mean())) < 1e-9
+
+
+@pytest.mark.gpu
+def test_graphed_step_replays_the_eager_step_bit_for_bit():
+    """mgproto_b200.pipeline.GraphedStep (head forward + loss + backward + enqueue + update_GMM in one CUDA graph)
+    against the same sequence of eager steps on a twin model: logits, feature gradient, means, mixture weights, bank and
+    the Adam step count must be identical -- every piece of step-dependent state lives on the device."""
+    import copy
+    import mgproto_b200 as M
+    from mgproto_b200 import ops
+    from mgproto_b200.pipeline import GraphedStep
+    torch.manual_seed(3)
+    C, K, D, T, cap, B, H = 6, 4, 128, 4, 8, 16, 6
+    net_a = M.MGProto(features=nn.Sequential(nn.Conv2d(3, 8, 1)), img_size=H, prototype_shape=(C * K, D, 1, 1),
+                      proto_layer_rf_info=None, num_classes=C, add_on_layers_type="regular", sz_embedding=8,
+                      mem_capacity=cap, mine_K=T).to(_dev())
+    net_b = copy.deepcopy(net_a)
+    for n in (net_a, net_b):
+        n.prototype_optimizer = torch.optim.Adam([{"params": n.prototype_means, "lr": 3e-3}])
+        n.train()
+    g = torch.Generator().manual_seed(4)
+    xs = [torch.randn(B, D, H, H, generator=g).to(_dev()) for _ in range(4)]
+    gts = [torch.randint(0, C, (B,), generator=g).to(_dev()) for _ in range(4)]
+
+    def loss_fn(out, gt):
+        return ops.mine_cross_entropy(out, gt, 0.2)
+
+    seq = [0, 0, 0, 1, 2, 3, 1]                      # warm-up (2) + 5 replays
+    for i in seq:
+        x = xs[i].clone().requires_grad_(True)
+        out_a = net_a.head(x, gts[i])
+        loss_a = loss_fn(out_a, gts[i])
+        loss_a.backward()
+        net_a.update_GMM()
+        grad_a = x.grad
+    step = GraphedStep(net_b, loss_fn, xs[0], gts[0], warmup=2)
+    assert step.launches >= 10
+    for i in seq[2:]:
+        v0 = net_b.prototype_means._version
+        out_b, loss_b = step(xs[i], gts[i])
+        assert net_b.prototype_means._version > v0
+    torch.cuda.synchronize()
+    assert torch.equal(out_b, out_a) and torch.equal(loss_b, loss_a) and torch.equal(step.x_grad, grad_a)
+    assert torch.equal(net_b.prototype_means, net_a.prototype_means)
+    assert torch.equal(net_b.last_layer.weight, net_a.last_layer.weight)
+    assert torch.equal(net_b.queue.bank, net_a.queue.bank) and torch.equal(net_b.queue.mem_len, net_a.queue.mem_len)
+    net_a.sync_optimizer_state()
+    net_b.sync_optimizer_state()
+    sa = net_a.prototype_optimizer.state[net_a.prototype_means]
+    sb = net_b.prototype_optimizer.state[net_b.prototype_means]
+    assert int(sa["step"]) == int(sb["step"]) and int(sa["step"]) > 0
+    assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"])

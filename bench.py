@@ -767,7 +767,31 @@ def main():
         line.update(extra)
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators must outlive every CUDA graph that captured their kernels: drop the graph first; and a rank
+        # that is done (ranks > 0 skip the single-GPU legs) must never be able to hang the launcher -- the teardown runs
+        # in a thread and the process leaves with os._exit whatever it does
+        import threading
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if graphed is not None:
+            try:
+                graphed.close()
+            except Exception:                                     # noqa: BLE001
+                pass
+        graphed = None
+        torch.cuda.synchronize()
+
+        def _teardown():
+            try:
+                dist.destroy_process_group()
+            except Exception:                                     # noqa: BLE001
+                pass
+
+        th = threading.Thread(target=_teardown, daemon=True)
+        th.start()
+        th.join(20.0)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -120,6 +120,12 @@ class GraphedStep:
         self.launches = ops.launch_count() - n0      # library kernels per replay (torch's own few are not counted)
         self.x_grad = self.x.grad
 
+    def close(self):
+        """Release the captured graph (and its private memory pool).  With torch.distributed: call it before
+        destroy_process_group -- NCCL communicators must outlive the graphs that captured their kernels."""
+        self.graph.reset()
+        self.out = self.loss = self.x_grad = None
+
     def _body(self):
         self.x.grad = None
         out = self.net.head(self.x, self.gt)

@@ -653,10 +653,28 @@ def main():
             torch.cuda.synchronize()
             t_ug = e0.elapsed_time(e1) / reps / 1e3
             ub = Lp * eb
+            # ... and with the classes one 256-image batch touches (what the timed step runs: <= #SMs active classes
+            # take the software-pipelined kernel, more take the serial one)
+            flags = torch.zeros_like(net.queue.updated)
+            flags[torch.unique(gts[0])] = 1
+            n_batch_active = int(flags.sum())
+            for _ in range(3):
+                net.queue.updated.copy_(flags)
+                net.update_GMM()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                net.queue.updated.copy_(flags)
+                net.update_GMM()
+            e1.record()
+            torch.cuda.synchronize()
+            t_ub = e0.elapsed_time(e1) / reps / 1e3
             extra["roofline_step_update_gmm"] = {
                 "kernel": "update_GMM = em_plan + em_tc_kernel (tcgen05; 200 active classes, %d EM loops; + one fill)" % Lp,
                 "bound": "hbm", "achieved": ub / t_ug / 1e9, "peak": peak, "unit": "GB/s", "frac": ub / t_ug / 1e9 / peak,
                 "us_per_call": t_ug * 1e6, "algorithmic_bytes": ub,
+                "batch_active_classes": n_batch_active, "us_per_call_batch_active": t_ub * 1e6,
+                "frac_batch_active": ub * n_batch_active / float(flags.numel()) / t_ub / 1e9 / peak,
                 "note": "latency-bound chain per class (DESIGN.md 5.3): one CTA per class, 7 row tiles x 3 loops; the bank's "
                         "fp16 hi/lo shadow (same bytes as the fp32 bank) is re-read per EM loop, L2-resident after the first"}
         except Exception as ex:  # noqa: BLE001 -- an auxiliary figure must never cost the bench line

@@ -1,9 +1,9 @@
 // a2 (compute_log_prob, [N,P] output) on the tensor cores with the PATCH tile resident in tensor memory.
 //
-// logprob_tc.cu feeds both operands of every tcgen05.mma from shared memory (8 KB per 128x128x16 MMA = the whole
-// 128 B/clk of the SM) and stages the output through shared memory as well; shared-memory bandwidth, not the tensor
-// pipe or HBM, bounds it (profiles/: 0.65 of the HBM roof, MMAs alone 75 us of a 33 us tensor floor), and it needs a
-// separate pass that splits x into fp16 hi/lo operands in HBM (+20 us at op level).  Here:
+// logprob_tc.cu feeds both operands of every tcgen05.mma from shared memory and stages the output through shared memory
+// as well; operand fetch + ring writes + the output stage oversubscribe the SM's shared-memory bandwidth (profiles/:
+// 0.65 of the HBM roof for the kernel, 0.52 for the op), and it needs a separate pass that splits x into fp16 hi/lo
+// operands in HBM.  Here:
 //   * the fp32 patch tile [128 x D] is TMA-loaded as it is (no operand pre-pass over x: the split is fused), the eight
 //     epilogue warps convert it in registers to fp16 hi / lo of 256 x and write it with tcgen05.st into TENSOR MEMORY,
 //     where it stays as the A operand (lane = patch) of the 3 * D/16 MMAs of every prototype tile the CTA visits;
@@ -12,13 +12,16 @@
 //     TMA / mbarrier ring in shared memory: 4 KB of operand reads per MMA instead of 8;
 //   * TMEM lane = patch, column = prototype, so an epilogue thread holds 32 consecutive floats of ONE output row and
 //     hands them, via a 4 KB per-warp block written with eight conflict-free STS.128, to an asynchronous TMA store
-//     (plain LSU stores from only 8 warps per SM back-pressure at ~3.5 TB/s: measured, profiles/).
-// Shared-memory traffic per 128 x 128 output tile drops from ~400 KB to ~160 KB (below the tensor pipe's 1536 clk), so
-// the kernel is bound by the HBM write stream of log p.
+//     (plain LSU stores from only 8 warps per SM back-pressure at ~3.5 TB/s: measured, profiles/);
+//   * balanced schedule: CTA i owns the pairs [i U / G, (i+1) U / G) of the x-major list of (x tile, prototype tile)
+//     pairs, so every CTA gets U / G pairs +- 1 however the x tiles divide by the grid.
+// The kernel is bound by the HBM write stream of log p (profiles/r2_ka_ablation.txt).
 //
 // Shapes: sigma constant over d inside every prototype (inner dimension K = D; the caller asserts it, the kernel traps
-// if the prototype pre-pass says otherwise) and D in {64, 128} (A double-buffered in TMEM: 2 * D columns + 2 * 128
-// accumulator columns <= 512).  Everything else takes logprob_tc.cu.
+// if the prototype pre-pass says otherwise) and D in {64, 128, 256}: 2 * 128 accumulator columns + the operand buffers
+// must fit the 512 TMEM columns -- two buffers of D columns for D <= 128 (the next tile is converted under the MMAs of
+// the current one), ONE buffer of 256 columns for D = 256 (the fp32 tile then lands and is converted in two halves,
+// after the current tile's MMAs have retired).  Everything else takes logprob_tc.cu.
 //
 // Warps: 0 prototype TMA producer | 1 MMA issuer (one thread, TS form: A from TMEM) | 2 TMEM allocator + x TMA producer
 //        | 3 idle | 4..11 converter + epilogue: warp = TMEM lane quarter (w & 3); group (w >> 2) converts one column half

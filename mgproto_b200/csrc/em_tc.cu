@@ -17,10 +17,16 @@
 // classes' steps) is fp32 SIMT on the class's state, which stays in registers / shared memory for the whole timeline
 // exactly as in em_fused_kernel (em.cu); thread d owns mean / moment elements (k, d) for all k.
 //
-// Pipeline per 128-row tile: TMA load (mbarrier) -> 3*D/16 E-step MMAs -> epilogue (tcgen05.ld, soft-max, R) ->
-// 3*D/16 statistics MMAs accumulating in TMEM across the tiles of the loop.  One tile buffer per CTA; two CTAs per SM
-// (D = 128) overlap each other's latencies.  HBM/L2 traffic: num_em_loop x (4 D + 4) bytes per bank row -- the
-// algorithmic bytes of SURVEY 8(d) K-D.
+// Per 128-row tile: TMA load (mbarrier) -> 2*D/16 E-step MMAs (hi rows 0-15 and lo rows 16-31 of the means share one
+// B block: one N = 32 and one N = 16 MMA per k-step) -> epilogue (tcgen05.ld, soft-max, R) -> 2*128/16 statistics MMAs
+// accumulating in TMEM across the tiles of the loop.  Two variants of the same kernel (template flag PIPE):
+//   * serial (D = 256; D = 128 when more classes are active than there are SMs): the phases of a tile run one after
+//     the other on one tile buffer, two CTAs per SM (D = 128) overlap each other's latencies;
+//   * pipelined (D = 128, one CTA per SM, classes in the planner's order): three tile buffers, two E-step accumulators
+//     and two R buffers; one thread issues TMA(t+1), the E-step MMAs of tile t and the statistics MMAs of tile t-1
+//     while warps 0-3 run the soft-max of tile t; idle warps apply the replay of inactive classes.
+// Both are enqueued and the planner's count of active classes decides on the device which one does the work.
+// HBM/L2 traffic: num_em_loop x (4 D + 4) bytes per bank row -- the algorithmic bytes of SURVEY 8(d) K-D.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
